@@ -1,0 +1,211 @@
+"""The benchmark / parity scenarios of BASELINE.json (``configs[0..4]``) and their
+seeded synthetic initial states.
+
+Builders take the module namespace to build with (``api``): this package by
+default, or the real reference when ``oracle/make_goldens.py`` generates the
+fixtures -- the same function therefore defines the scenario for both sides.
+Initial states are numpy on the host; the GPU path uploads them.
+"""
+import numpy as np
+
+from . import homogeneousmatrix as Hg
+
+SEED0 = 20260000
+SNAKE_LENGTHS = [1., .9, .8, .7, .6, .5, .4, .3, .2]   # matlab/test_snake.py:47-58
+SNAKE_QREF = 0.25                                     # arc the loop is closed on
+KNEE_LIMITS = (-2.4, 0.05)
+
+
+def snake_tip(q):
+    """Tip position of the planar snake (base at the origin) for hinge angles q."""
+    th = np.cumsum(q)
+    L = np.asarray(SNAKE_LENGTHS)
+    return float(-(L*np.sin(th)).sum()), float((L*np.cos(th)).sum())
+
+
+class _Api(object):
+    """Names a scenario needs, resolved from this package or the reference."""
+
+    def __init__(self, reference=False):
+        if reference:
+            import arboris.core as core
+            import arboris.constraints as constraints
+            import arboris.controllers as controllers
+            from arboris.robots import human36, simplearm, snake, simpleshapes
+        else:
+            from . import core, constraints, controllers
+            from .robots import human36, simplearm, snake, simpleshapes
+        self.core, self.constraints, self.controllers = core, constraints, controllers
+        self.human36, self.simplearm, self.snake = human36, simplearm, snake
+        self.simpleshapes = simpleshapes
+
+
+def simplearm_world(reference=False):
+    """configs[0]: 3-dof planar arm under gravity, shoulder at 3.14/4
+    (the recipe of tests/test_visu_collada.py:11-27)."""
+    a = _Api(reference)
+    w = a.core.World()
+    w.register(a.controllers.WeightController())
+    a.simplearm.add_simplearm(w)
+    w.getjoints()['Shoulder'].gpos[0] = 3.14/4
+    w.init()
+    return w
+
+
+def human36_free_world(reference=False):
+    """configs[1]: free-floating humanoid under gravity, no constraints."""
+    a = _Api(reference)
+    w = a.core.World()
+    a.human36.add_human36(w)
+    w.register(a.controllers.WeightController())
+    w.init()
+    return w
+
+
+def human36_contact_world(reference=False):
+    """configs[2] and [4]: humanoid over a ground plane, 8 SoftFingerContact
+    (mu = .6, tests/test_human36_falling.py:13-38) then JointLimits on the two
+    1-dof knees."""
+    a = _Api(reference)
+    w = a.core.World()
+    a.simpleshapes.add_groundplane(w)
+    a.human36.add_human36(w)
+    w.register(a.controllers.WeightController())
+    for c in a.constraints.get_all_contacts(w, friction_coeff=.6):
+        w.register(c)
+    joints = list(w.iterjoints())
+    for k in (2, 5):   # ShankR, ShankL knees: dofs 9 and 15
+        assert joints[k].ndof == 1
+        w.register(a.constraints.JointLimits(joints[k], *KNEE_LIMITS))
+    w.init()
+    return w
+
+
+def snake_loop_world(reference=False):
+    """configs[3]: free 9-link snake whose base and tip are pinned to the
+    ground by two BallAndSocketConstraint (a kinematic loop)."""
+    a = _Api(reference)
+    w = a.core.World()
+    n = len(SNAKE_LENGTHS)
+    a.snake.add_snake(w, n, lengths=list(SNAKE_LENGTHS), masses=list(SNAKE_LENGTHS),
+                      gpos=[0.]*n, gvel=[0.]*n, is_fixed=False)
+    w.register(a.controllers.WeightController())
+    joints = list(w.iterjoints())
+    base = joints[0]._frame1.body
+    tip = w._subframes[-1]          # the frame add_snake registers last
+    # the loop is closed on the arc q_i = SNAKE_QREF (a straight chain between two
+    # pins would be a singular configuration)
+    tx, ty = snake_tip([SNAKE_QREF]*n)
+    tip_pose0 = Hg.transl(tx, ty, 0.)
+    w.register(a.constraints.BallAndSocketConstraint(frames=(w.ground, base)))
+    w.register(a.constraints.BallAndSocketConstraint(
+        frames=(a.core.SubFrame(w.ground, tip_pose0), tip)))
+    w.init()
+    return w
+
+
+def ball_socket_world(reference=False):
+    """tests/test_constraints.py:39-47: a unit-mass free body hung from the
+    ground by a ball and socket, under gravity."""
+    a = _Api(reference)
+    w = a.core.World()
+    if reference:
+        from arboris.joints import FreeJoint
+    else:
+        from .joints import FreeJoint
+    b0 = a.core.Body(mass=np.eye(6))
+    w.add_link(w.ground, FreeJoint(), b0)
+    w.register(a.controllers.WeightController())
+    w.register(a.constraints.BallAndSocketConstraint(frames=(w.ground, b0)))
+    w.init()
+    return w
+
+
+def simplearm_limits_world(reference=False, shoulder=3.14/2 - 0.1):
+    """tests/test_constraints.py:11-32: JointLimits on the shoulder."""
+    a = _Api(reference)
+    w = a.core.World()
+    a.simplearm.add_simplearm(w)
+    w.register(a.controllers.WeightController())
+    sh = w.getjoints()['Shoulder']
+    w.register(a.constraints.JointLimits(sh, -3.14/2, 3.14/2))
+    sh.gpos[0] = shoulder
+    w.init()
+    return w
+
+
+BUILDERS = {
+    "simplearm": simplearm_world,
+    "human36_free": human36_free_world,
+    "human36_contact": human36_contact_world,
+    "snake_loop": snake_loop_world,
+    "ball_socket": ball_socket_world,
+    "simplearm_limits": simplearm_limits_world,
+}
+
+
+# ---------------------------------------------------------------------------
+# seeded initial states, per world index (numpy, host)
+# ---------------------------------------------------------------------------
+def _free_and_linear(model):
+    free = [j for j in range(len(model.joint_type)) if int(model.joint_type[j]) == 0]
+    lin = np.ones(model.ngpos, bool)
+    for j in free:
+        g = int(model.joint_gpos[j])
+        lin[g:g + 16] = False
+    return free, lin
+
+
+def initial_state(model, scenario, w):
+    """(gpos, gvel) of world ``w`` for ``scenario``; deterministic in ``w``."""
+    rng = np.random.default_rng(SEED0 + int(w))
+    gpos = np.array(model.gpos0, dtype=float)
+    gvel = np.array(model.gvel0, dtype=float)
+    free, lin = _free_and_linear(model)
+    if scenario == "human36_free":
+        gpos[lin] = rng.uniform(-0.5, 0.5, int(lin.sum()))
+        t = rng.uniform([-.1, 0., -.1], [.1, .2, .1])
+        r = rng.uniform(-.3, .3, 3)
+        g = int(model.joint_gpos[free[0]])
+        H0 = gpos[g:g + 16].reshape(4, 4)
+        gpos[g:g + 16] = np.dot(np.dot(Hg.transl(*t), Hg.rotzyx(*r)), H0).reshape(-1)
+        gvel[:] = rng.uniform(-1., 1., model.ndof)
+    elif scenario == "human36_contact":
+        gpos[lin] = rng.uniform(-0.1, 0.1, int(lin.sum()))
+        lift = rng.uniform(0.02, 0.07)
+        r = rng.uniform(-.02, .02, 3)
+        g = int(model.joint_gpos[free[0]])
+        H0 = gpos[g:g + 16].reshape(4, 4)
+        # lift is left-multiplied as in tests/test_human36_falling.py:16-18
+        gpos[g:g + 16] = np.dot(Hg.transl(0., lift, 0.),
+                                np.dot(H0, Hg.rotzyx(*r))).reshape(-1)
+    elif scenario == "snake_loop":
+        # start (almost) on the closed loop: a large loop error would be
+        # corrected within one dt by BallAndSocketConstraint.solve and diverge
+        gpos[lin] = SNAKE_QREF + rng.uniform(-1e-3, 1e-3, int(lin.sum()))
+        gvel[:] = rng.uniform(-.2, .2, model.ndof)
+    elif scenario in ("simplearm", "ball_socket", "simplearm_limits"):
+        if w > 0:
+            gpos[lin] += rng.uniform(-0.2, 0.2, int(lin.sum()))
+            gvel[:] = rng.uniform(-.5, .5, model.ndof)
+    else:
+        raise KeyError(scenario)
+    if scenario != "simplearm_limits":
+        # keep limited joints strictly inside their limits (outside the
+        # activation band) so that no world starts in violation
+        for c in range(len(model.cons_type)):
+            if int(model.cons_type[c]) == 0:
+                g = int(model.cons_int[c][2])
+                mn, mx, prox = model.cons_dbl[c][0:3]
+                gpos[g] = min(max(gpos[g], mn + 2*prox), mx - 2*prox)
+    return gpos, gvel
+
+
+def initial_states(model, scenario, w0, w1):
+    """Stacked states of worlds ``w0..w1-1``: gpos (ngpos, W), gvel (ndof, W)."""
+    W = w1 - w0
+    gpos = np.empty((model.ngpos, W))
+    gvel = np.empty((model.ndof, W))
+    for i in range(W):
+        gpos[:, i], gvel[:, i] = initial_state(model, scenario, w0 + i)
+    return gpos, gvel
