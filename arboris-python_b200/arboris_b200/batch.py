@@ -1,0 +1,274 @@
+"""``BatchedWorld``: W independent worlds of one model stepping in lockstep on a GPU.
+
+It exposes the reference's step API (``update_dynamic``, ``update_controllers``,
+``update_constraints``, ``integrate``, and ``simulate()`` via
+``arboris_b200.core.simulate``; reference core.py:682-980, 1334-1365) over
+batched state, plus the fused ``step``.  PyTorch owns the device memory and the
+stream; all arithmetic is in the CUDA library behind the C ABI
+(``include/arboris_b200.h``), loaded with ctypes.  No CUDA library or no GPU ->
+this module raises; there is no CPU path.
+
+State tensors (fp64, device, world index fastest -- the layout the kernels
+coalesce on):  ``gpos`` (ngpos, W), ``gvel`` (ndof, W), ``cforce`` (nrows, W).
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+from .flatten import FlatModel, flatten, JOINT_NDOF, JOINT_NGPOS
+
+MATRIX_IDS = {"mass": 0, "nleffects": 1, "viscosity": 2, "impedance": 3, "admittance": 4}
+BODY_IDS = {"pose": (0, (4, 4)), "twist": (1, (6,)), "jacobian": (2, None),
+            "djacobian": (3, None), "nleffects": (4, (6, 6))}
+
+
+class BatchedWorld(object):
+    def __init__(self, world_or_model, nworlds=1, device=None, stream=None):
+        if isinstance(world_or_model, FlatModel):
+            self.world, self.model = None, world_or_model
+        else:
+            self.world = world_or_model
+            if hasattr(world_or_model, "init") and getattr(world_or_model, "_ndof", 0) == 0:
+                world_or_model.init()
+            self.model = flatten(world_or_model)
+        if not torch.cuda.is_available():
+            raise RuntimeError("arboris_b200 needs a CUDA device: the simulation step has no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        self.nworlds = int(nworlds)
+        self._lib = _capi.load()
+        m = self.model
+        self._desc, self._keep = _capi.make_desc(m)
+        h = C.c_void_p()
+        _capi.check(self._lib, self._lib.arb_model_create(C.byref(self._desc), C.byref(h)))
+        self._model_h = h
+        self._stream = stream
+        with torch.cuda.device(self.device):
+            s = torch.cuda.current_stream(self.device) if stream is None else stream
+            b = C.c_void_p()
+            _capi.check(self._lib, self._lib.arb_batch_create(
+                self._model_h, self.nworlds, self.device.index or 0,
+                C.c_void_p(s.cuda_stream), C.byref(b)))
+        self._batch_h = b
+        W = self.nworlds
+        kw = dict(dtype=torch.float64, device=self.device)
+        self.gpos = torch.empty((m.ngpos, W), **kw)
+        self.gvel = torch.empty((m.ndof, W), **kw)
+        self.cforce = torch.zeros((max(int(m.nrows), 1), W), **kw)
+        self._bind()
+        self.set_state(np.repeat(np.asarray(m.gpos0)[:, None], W, 1),
+                       np.repeat(np.asarray(m.gvel0)[:, None], W, 1),
+                       np.repeat(np.asarray(m.cforce0)[:, None], W, 1) if m.nrows else None)
+        self._current_time = 0.
+        self._pinned = None
+
+    # ---- plumbing -----------------------------------------------------------------
+    def _bind(self):
+        _capi.check(self._lib, self._lib.arb_batch_bind_state(
+            self._batch_h, self.gpos.data_ptr(), self.gvel.data_ptr(), self.cforce.data_ptr()))
+
+    def _sync_stream(self):
+        s = torch.cuda.current_stream(self.device) if self._stream is None else self._stream
+        self._lib.arb_batch_set_stream(self._batch_h, C.c_void_p(s.cuda_stream))
+
+    def close(self):
+        if getattr(self, "_batch_h", None):
+            self._lib.arb_batch_destroy(self._batch_h)
+            self._batch_h = None
+        if getattr(self, "_model_h", None):
+            self._lib.arb_model_destroy(self._model_h)
+            self._model_h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    ndof = property(lambda self: int(self.model.ndof))
+    current_time = property(lambda self: self._current_time)
+
+    def init(self):
+        """``World.init()`` of the batched world: the model is already flat."""
+
+    # ---- state ----------------------------------------------------------------------
+    def set_state(self, gpos=None, gvel=None, cforce=None):
+        """Upload state given as (elem, W) arrays (numpy or torch)."""
+        for dst, src in ((self.gpos, gpos), (self.gvel, gvel), (self.cforce, cforce)):
+            if src is None:
+                continue
+            t = torch.as_tensor(np.ascontiguousarray(src) if isinstance(src, np.ndarray) else src,
+                                dtype=torch.float64)
+            if t.numel() == 0:
+                continue
+            dst[:t.shape[0]].copy_(t.reshape(t.shape[0], -1), non_blocking=False)
+
+    def get_state(self):
+        return self.gpos.cpu().numpy(), self.gvel.cpu().numpy(), \
+            self.cforce[:int(self.model.nrows)].cpu().numpy()
+
+    # ---- the four phases and the fused step ---------------------------------------------
+    def update_dynamic(self):
+        self._sync_stream()
+        _capi.check(self._lib, self._lib.arb_update_dynamic(self._batch_h))
+
+    def update_controllers(self, dt):
+        assert dt > 0
+        self._sync_stream()
+        _capi.check(self._lib, self._lib.arb_update_controllers(self._batch_h, float(dt)))
+
+    def update_constraints(self, dt):
+        assert dt > 0
+        self._sync_stream()
+        _capi.check(self._lib, self._lib.arb_update_constraints(self._batch_h, float(dt)))
+
+    def integrate(self, dt):
+        assert dt > 0
+        self._sync_stream()
+        _capi.check(self._lib, self._lib.arb_integrate(self._batch_h, float(dt)))
+        self._current_time += dt
+
+    def step(self, dt, nsteps=1):
+        """``nsteps`` iterations of the simulate() loop, fused on the device."""
+        dts = np.full(nsteps, dt, dtype=np.float64) if np.isscalar(dt) else \
+            np.ascontiguousarray(dt, dtype=np.float64)
+        self._sync_stream()
+        _capi.check(self._lib, self._lib.arb_step(
+            self._batch_h, dts.ctypes.data_as(_capi.c_dblp), len(dts)))
+        self._current_time += float(dts.sum())
+
+    def step_host(self, gpos, gvel, cforce, dt, nsteps=1):
+        """End-to-end call with HOST buffers (numpy (elem, W), updated in place):
+        host->device copy of the state, ``nsteps`` steps, device->host copy."""
+        dts = np.full(nsteps, dt, dtype=np.float64)
+        self._sync_stream()
+        cf = cforce.ctypes.data if cforce is not None and cforce.size else None
+        _capi.check(self._lib, self._lib.arb_step_host(
+            self._batch_h, gpos.ctypes.data, gvel.ctypes.data, cf,
+            dts.ctypes.data_as(_capi.c_dblp), nsteps))
+        self._current_time += float(dts.sum())
+
+    # ---- read-backs --------------------------------------------------------------------------
+    def _range(self, w0, w1):
+        w1 = self.nworlds if w1 is None else w1
+        return int(w0), int(w1)
+
+    def matrix(self, name, w0=0, w1=None):
+        """(w1-w0, n, n) tensor of ``mass|nleffects|viscosity|impedance|admittance``."""
+        w0, w1 = self._range(w0, w1)
+        n = self.ndof
+        out = torch.empty((w1 - w0, n, n), dtype=torch.float64, device=self.device)
+        self._sync_stream()
+        _capi.check(self._lib, self._lib.arb_get_matrix(
+            self._batch_h, MATRIX_IDS[name], out.data_ptr(), w0, w1))
+        return out
+
+    mass = property(lambda self: self.matrix("mass"))
+    nleffects = property(lambda self: self.matrix("nleffects"))
+    viscosity = property(lambda self: self.matrix("viscosity"))
+    impedance = property(lambda self: self.matrix("impedance"))
+    admittance = property(lambda self: self.matrix("admittance"))
+
+    def gforce(self, w0=0, w1=None):
+        w0, w1 = self._range(w0, w1)
+        out = torch.empty((w1 - w0, self.ndof), dtype=torch.float64, device=self.device)
+        self._sync_stream()
+        _capi.check(self._lib, self._lib.arb_get_vector(self._batch_h, 0, out.data_ptr(), w0, w1))
+        return out
+
+    def body(self, what, body, w0=0, w1=None):
+        """``pose|twist|jacobian|djacobian|nleffects`` of body index ``body``
+        (0 = ground) for worlds [w0, w1)."""
+        w0, w1 = self._range(w0, w1)
+        code, shape = BODY_IDS[what]
+        if shape is None:
+            shape = (6, self.ndof)
+        out = torch.empty((w1 - w0,) + shape, dtype=torch.float64, device=self.device)
+        self._sync_stream()
+        _capi.check(self._lib, self._lib.arb_get_body(
+            self._batch_h, code, int(body), out.data_ptr(), w0, w1))
+        return out
+
+    def constraints(self, what, w0=0, w1=None):
+        """``active|branch`` (int32 (W, nc)), ``sdist`` (fp64 (W, nc)) or
+        ``zidx`` (int32 (W, nc, 3))."""
+        w0, w1 = self._range(w0, w1)
+        nc = len(self.model.cons_type)
+        code = {"active": 0, "branch": 1, "sdist": 2, "zidx": 3}[what]
+        if what == "sdist":
+            out = torch.zeros((w1 - w0, nc), dtype=torch.float64, device=self.device)
+        elif what == "zidx":
+            out = torch.zeros((w1 - w0, nc, 3), dtype=torch.int32, device=self.device)
+        else:
+            out = torch.zeros((w1 - w0, nc), dtype=torch.int32, device=self.device)
+        if nc:
+            self._sync_stream()
+            _capi.check(self._lib, self._lib.arb_get_constraint(
+                self._batch_h, code, out.data_ptr(), w0, w1))
+        return out
+
+    def status(self):
+        """Per-world ARB_STATUS_* bits accumulated since the last call."""
+        out = torch.zeros(self.nworlds, dtype=torch.int32, device=self.device)
+        self._sync_stream()
+        _capi.check(self._lib, self._lib.arb_batch_status(self._batch_h, out.data_ptr()))
+        return out
+
+    def launch_count(self):
+        return int(self._lib.arb_batch_launch_count(self._batch_h))
+
+    # ---- single-world synchronisation used by World.update_* ------------------------------
+    def push_host_state(self, world):
+        m = self.model
+        gpos = np.zeros(m.ngpos)
+        for k, j in enumerate(world.iterjoints()):
+            v = np.asarray(j.gpos, dtype=float).reshape(-1)
+            gpos[int(m.joint_gpos[k]):int(m.joint_gpos[k]) + v.size] = v
+        cf = np.zeros(max(int(m.nrows), 1))
+        for k, c in enumerate(world._constraints):
+            f = np.asarray(c._force, dtype=float).reshape(-1)
+            cf[int(m.cons_row[k]):int(m.cons_row[k]) + f.size] = f
+        self.set_state(gpos[:, None], np.asarray(world._gvel, dtype=float)[:, None], cf[:, None])
+
+    def pull_dynamic(self, world):
+        world._mass[:] = self.matrix("mass")[0].cpu().numpy()
+        world._nleffects[:] = self.matrix("nleffects")[0].cpu().numpy()
+        world._viscosity[:] = self.matrix("viscosity")[0].cpu().numpy()
+        for k, b in enumerate(world.iterbodies()):
+            b._pose = self.body("pose", k)[0].cpu().numpy()
+            b._twist = self.body("twist", k)[0].cpu().numpy()
+            b._jacobian = self.body("jacobian", k)[0].cpu().numpy()
+            b._djacobian = self.body("djacobian", k)[0].cpu().numpy()
+            b._nleffects = self.body("nleffects", k)[0].cpu().numpy()
+
+    def pull_controllers(self, world):
+        world._impedance = self.matrix("impedance")[0].cpu().numpy()
+        world._admittance = self.matrix("admittance")[0].cpu().numpy()
+        world._gforce[:] = self.gforce()[0].cpu().numpy()
+
+    def pull_constraints(self, world):
+        m = self.model
+        world._gforce[:] = self.gforce()[0].cpu().numpy()
+        cf = self.cforce[:, 0].cpu().numpy()
+        act = self.constraints("active")[0].cpu().numpy()
+        sd = self.constraints("sdist")[0].cpu().numpy()
+        for k, c in enumerate(world._constraints):
+            r0 = int(m.cons_row[k])
+            c._force[:] = cf[r0:r0 + c._force.size]
+            c._is_active = bool(act[k])
+            if hasattr(c, "_sdist"):
+                c._sdist = float(sd[k])
+
+    def pull_state(self, world):
+        m = self.model
+        gpos = self.gpos[:, 0].cpu().numpy()
+        world._gvel[:] = self.gvel[:, 0].cpu().numpy()
+        for k, j in enumerate(world.iterjoints()):
+            g = int(m.joint_gpos[k])
+            t = int(m.joint_type[k])
+            if t == 0:
+                j.gpos = gpos[g:g + 16].reshape(4, 4).copy()
+            else:
+                j.gpos[:] = gpos[g:g + JOINT_NDOF[t]]

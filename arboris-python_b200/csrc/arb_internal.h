@@ -1,0 +1,38 @@
+// Library-private definitions of the opaque ABI handles.
+#pragma once
+#include <cuda_runtime.h>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+#include "arb_model_host.h"
+#include "arb_types.h"
+
+struct arb_model {
+  HostModel host;
+  std::map<int, DevModel> dev;                 // per CUDA device
+  std::map<int, std::vector<void*>> dev_owned;
+  std::set<int> dev_ready;
+};
+
+struct FusedState;  // arb_fused.cu
+
+struct arb_batch {
+  arb_model* model = nullptr;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  DevModel m;
+  DevBatch d;
+  double* scratch_dbl = nullptr;   // phase-API scratch (lazy)
+  int* scratch_int = nullptr;
+  int64_t launches = 0;
+  int force_phases = 0;            // tests: run arb_step through the four phase kernels
+  FusedState* fused = nullptr;
+};
+
+const char* arb_set_error(const std::string& s);
+int arb_step_phases(arb_batch* b, const double* dts, int nsteps);
+// warp-per-world fused step (arb_fused.cu)
+bool arb_fused_supported(const arb_batch* b);
+int arb_fused_step(arb_batch* b, const double* dts, int nsteps);
+void arb_fused_release(arb_batch* b);

@@ -1,0 +1,153 @@
+// Host-side preprocessing of an arb_model_desc into the tables the kernels read
+// (inverse constant frames, packed Jacobian column layout, body flags).  Plain
+// C++, shared by the CUDA library (arb_api.cu) and the CPU unit-test build.
+#pragma once
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "arb_math.cuh"
+#include "arb_types.h"
+
+struct HostModel {
+  int ndof = 0, ngpos = 0, nj = 0, nc = 0, na = 0, nrows = 0, ncols = 0, maxk = 0, anyvisc = 0;
+  std::vector<int> jtype, jparent, jdof, jgpos, hcn_ident, bflags, coloff, kcols, pathdof;
+  std::vector<int> ctype, cint, crow, atype, aint;
+  std::vector<double> Hpr, HprInv, Hcn, HcnInv, bmass, bvisc, brx, cdbl, adbl, ablob;
+  double up[3] = {0., 1., 0.};
+};
+
+static inline void se3_to12(const Se3& h, double* o) {
+  for (int i = 0; i < 9; ++i) o[i] = h.R[i];
+  for (int i = 0; i < 3; ++i) o[9 + i] = h.p[i];
+}
+
+static inline int build_host_model(const arb_model_desc* d, HostModel& m, std::string& err) {
+  if (!d) { err = "null model description"; return -1; }
+  if (d->njoints < 0 || d->ndof < 0 || d->nconstraints < 0 || d->ncontrollers < 0) {
+    err = "negative size in model description"; return -1;
+  }
+  m.ndof = d->ndof; m.ngpos = d->ngpos; m.nj = d->njoints; m.nc = d->nconstraints;
+  m.na = d->ncontrollers; m.nrows = d->nrows;
+  const int nj = m.nj;
+  m.jtype.assign(d->joint_type, d->joint_type + nj);
+  m.jparent.assign(d->joint_parent, d->joint_parent + nj);
+  m.jdof.assign(d->joint_dof, d->joint_dof + nj);
+  m.jgpos.assign(d->joint_gpos, d->joint_gpos + nj);
+  m.Hpr.resize(12 * nj); m.HprInv.resize(12 * nj); m.Hcn.resize(12 * nj); m.HcnInv.resize(12 * nj);
+  m.hcn_ident.resize(nj);
+  m.bmass.assign(d->body_mass, d->body_mass + 36 * nj);
+  m.bvisc.assign(d->body_visc, d->body_visc + 36 * nj);
+  m.brx.assign(9 * nj, 0.);
+  m.bflags.assign(nj, 0);
+  m.coloff.assign(nj + 1, 0);
+  m.kcols.assign(nj + 1, 0);
+  int ndof = 0, ngpos = 0;
+  std::vector<std::vector<int>> path(nj + 1);
+  for (int j = 0; j < nj; ++j) {
+    const int t = m.jtype[j];
+    if (t < 0 || t > ARB_JOINT_TXTYTZ) { err = "unknown joint type"; return -2; }
+    const int p = m.jparent[j];
+    if (p < 0 || p > j) { err = "joint parent must precede the joint (depth-first order)"; return -2; }
+    if (m.jdof[j] != ndof || m.jgpos[j] != ngpos) { err = "dof/gpos offsets are not contiguous"; return -2; }
+    ndof += arb_joint_ndof(t);
+    ngpos += arb_joint_ngpos(t);
+    Se3 h, hi;
+    se3_from16(d->joint_Hpr + 16 * j, h);
+    se3_inv(h, hi);
+    se3_to12(h, &m.Hpr[12 * j]);
+    se3_to12(hi, &m.HprInv[12 * j]);
+    se3_from16(d->joint_Hcn + 16 * j, h);
+    se3_inv(h, hi);
+    se3_to12(h, &m.Hcn[12 * j]);
+    se3_to12(hi, &m.HcnInv[12 * j]);
+    bool ident = true;
+    for (int i = 0; i < 16; ++i)
+      if (d->joint_Hcn[16 * j + i] != ((i % 5 == 0) ? 1. : 0.)) ident = false;
+    m.hcn_ident[j] = ident ? 1 : 0;
+    const double* M = &m.bmass[36 * j];
+    int fl = 0;
+    for (int i = 0; i < 36; ++i) {
+      if (M[i] > 0.) fl |= ARB_BODY_MASSIVE;
+      if (M[i] != 0.) fl |= ARB_BODY_HASMASS;
+      if (m.bvisc[36 * j + i] != 0.) fl |= ARB_BODY_HASVISC;
+    }
+    if (fl & ARB_BODY_HASVISC) m.anyvisc = 1;
+    m.bflags[j] = fl;
+    if (!(M[6 * 3 + 3] <= 1e-10))  // core.py:1280
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) m.brx[9 * j + 3 * r + c] = M[6 * r + 3 + c] / M[6 * 3 + 3];
+    path[j + 1] = path[p];
+    for (int i = 0; i < arb_joint_ndof(t); ++i) path[j + 1].push_back(m.jdof[j] + i);
+  }
+  if (ndof != m.ndof || ngpos != m.ngpos) { err = "ndof/ngpos do not match the joint list"; return -2; }
+  for (int b = 0; b <= nj; ++b) {
+    m.coloff[b] = (int)m.pathdof.size();
+    m.kcols[b] = (int)path[b].size();
+    if (m.kcols[b] > m.maxk) m.maxk = m.kcols[b];
+    m.pathdof.insert(m.pathdof.end(), path[b].begin(), path[b].end());
+  }
+  m.ncols = (int)m.pathdof.size();
+  m.ctype.assign(d->cons_type, d->cons_type + m.nc);
+  m.cint.assign(d->cons_int, d->cons_int + ARB_CONS_NINT * m.nc);
+  m.cdbl.assign(d->cons_dbl, d->cons_dbl + ARB_CONS_NDBL * m.nc);
+  m.crow.assign(d->cons_row, d->cons_row + m.nc);
+  int rows = 0;
+  for (int c = 0; c < m.nc; ++c) {
+    const int t = m.ctype[c];
+    if (t < 0 || t > ARB_CONS_SOFT_FINGER_PLANE_POINT) { err = "unknown constraint type"; return -3; }
+    if (m.crow[c] != rows) { err = "constraint rows are not contiguous"; return -3; }
+    rows += arb_cons_ndol(t);
+    const int* ci = &m.cint[ARB_CONS_NINT * c];
+    if (t == ARB_CONS_JOINT_LIMITS) {
+      if (ci[0] < 0 || ci[0] >= nj || arb_joint_ndof(m.jtype[ci[0]]) != 1) {
+        err = "JointLimits needs a 1-dof joint"; return -3;
+      }
+    } else if (ci[0] < 0 || ci[0] > nj || ci[1] < 0 || ci[1] > nj) {
+      err = "constraint body index out of range"; return -3;
+    }
+  }
+  if (rows != m.nrows) { err = "nrows does not match the constraint list"; return -3; }
+  m.atype.assign(d->ctrl_type, d->ctrl_type + m.na);
+  m.aint.assign(d->ctrl_int, d->ctrl_int + 4 * m.na);
+  m.adbl.assign(d->ctrl_dbl, d->ctrl_dbl + 4 * m.na);
+  if (d->nblob > 0) m.ablob.assign(d->ctrl_blob, d->ctrl_blob + d->nblob);
+  for (int a = 0; a < m.na; ++a)
+    if (m.atype[a] != ARB_CTRL_WEIGHT && m.atype[a] != ARB_CTRL_PD) { err = "unknown controller type"; return -4; }
+  for (int i = 0; i < 3; ++i) m.up[i] = d->up[i];
+  return 0;
+}
+
+// Sizes (in doubles / ints per world) of the per-batch scratch arrays, in the order
+// of the DevBatch members.
+struct ScratchSizes {
+  int64_t pose, twist, J, dJ, M, N, B, Z, Y, gforce, cjac, cvel, cA, cT, cpinv, caux, tmp;
+  int64_t cactive, cbranch, cdol, czidx;
+  int64_t total_doubles() const {
+    return pose + twist + J + dJ + M + N + B + Z + Y + gforce + cjac + cvel + cA + cT + cpinv + caux + tmp;
+  }
+  int64_t total_ints() const { return cactive + cbranch + cdol + czidx; }
+};
+static inline ScratchSizes scratch_sizes(const HostModel& m) {
+  ScratchSizes s;
+  const int64_t n = m.ndof, nj = m.nj, nr = m.nrows > 0 ? m.nrows : 1, nc = m.nc > 0 ? m.nc : 1;
+  s.pose = nj * 12; s.twist = nj * 6; s.J = (int64_t)m.ncols * 6; s.dJ = s.J;
+  s.M = s.N = s.B = s.Z = s.Y = n * n; s.gforce = n;
+  s.cjac = nr * n; s.cvel = nr; s.cA = nr * nr; s.cT = n * nr; s.cpinv = nr * 4; s.caux = nc * 4;
+  s.tmp = 2 * n;
+  s.cactive = s.cbranch = s.cdol = nc; s.czidx = nc * 3;
+  return s;
+}
+// carve `dbl` (doubles) and `ints` into the DevBatch members; W worlds
+static inline void carve_scratch(const ScratchSizes& s, int64_t W, double* dbl, int* ints, DevBatch& b) {
+  double* p = dbl;
+  auto take = [&](int64_t k) { double* r = p; p += k * W; return r; };
+  b.pose = take(s.pose); b.twist = take(s.twist); b.J = take(s.J); b.dJ = take(s.dJ);
+  b.M = take(s.M); b.N = take(s.N); b.B = take(s.B); b.Z = take(s.Z); b.Y = take(s.Y);
+  b.gforce = take(s.gforce); b.cjac = take(s.cjac); b.cvel = take(s.cvel); b.cA = take(s.cA);
+  b.cT = take(s.cT); b.cpinv = take(s.cpinv); b.caux = take(s.caux); b.tmp = take(s.tmp);
+  int* q = ints;
+  auto takei = [&](int64_t k) { int* r = q; q += k * W; return r; };
+  b.cactive = takei(s.cactive); b.cbranch = takei(s.cbranch); b.cdol = takei(s.cdol);
+  b.czidx = takei(s.czidx);
+}

@@ -1,0 +1,113 @@
+// TEST INFRASTRUCTURE ONLY.  CPU build of the per-world scalar routines of
+// arboris-python_b200/csrc (the same source the CUDA kernels compile), so that
+// `pytest -m "not gpu"` can check the arithmetic against the oracle without a
+// GPU.  Built by tests/hosttest/build.py into tests/hosttest/_build/; the
+// arboris_b200 package never loads it (the product path is CUDA only).
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../arboris-python_b200/csrc/arb_model_host.h"
+#include "../../arboris-python_b200/csrc/arb_world.cuh"
+
+static DevModel view(const HostModel& h) {
+  DevModel m;
+  m.ndof = h.ndof; m.ngpos = h.ngpos; m.nj = h.nj; m.nc = h.nc; m.na = h.na; m.nrows = h.nrows;
+  m.ncols = h.ncols; m.maxk = h.maxk; m.anyvisc = h.anyvisc;
+  m.jtype = h.jtype.data(); m.jparent = h.jparent.data(); m.jdof = h.jdof.data(); m.jgpos = h.jgpos.data();
+  m.Hpr = h.Hpr.data(); m.HprInv = h.HprInv.data(); m.Hcn = h.Hcn.data(); m.HcnInv = h.HcnInv.data();
+  m.hcn_ident = h.hcn_ident.data(); m.bmass = h.bmass.data(); m.bvisc = h.bvisc.data(); m.brx = h.brx.data();
+  m.bflags = h.bflags.data(); m.coloff = h.coloff.data(); m.kcols = h.kcols.data(); m.pathdof = h.pathdof.data();
+  m.ctype = h.ctype.data(); m.cint = h.cint.data(); m.crow = h.crow.data(); m.cdbl = h.cdbl.data();
+  m.atype = h.atype.data(); m.aint = h.aint.data(); m.adbl = h.adbl.data(); m.ablob = h.ablob.data();
+  for (int i = 0; i < 3; ++i) m.up[i] = h.up[i];
+  return m;
+}
+
+struct HostBatch {
+  HostModel hm;
+  DevModel dm;
+  DevBatch b;
+  std::vector<double> dbl;
+  std::vector<int> ints, status;
+};
+
+extern "C" {
+void* ht_create(const arb_model_desc* d, int64_t W, char* errbuf, int errlen) {
+  HostBatch* hb = new HostBatch();
+  std::string err;
+  if (build_host_model(d, hb->hm, err) != 0) {
+    strncpy(errbuf, err.c_str(), errlen - 1);
+    delete hb;
+    return nullptr;
+  }
+  hb->dm = view(hb->hm);
+  ScratchSizes s = scratch_sizes(hb->hm);
+  hb->dbl.assign(s.total_doubles() * W, 0.);
+  hb->ints.assign(s.total_ints() * W, 0);
+  hb->status.assign(W, 0);
+  memset(&hb->b, 0, sizeof(DevBatch));
+  hb->b.W = W;
+  carve_scratch(s, W, hb->dbl.data(), hb->ints.data(), hb->b);
+  hb->b.status = hb->status.data();
+  return hb;
+}
+void ht_destroy(void* p) { delete (HostBatch*)p; }
+void ht_bind(void* p, double* gpos, double* gvel, double* cforce) {
+  HostBatch* hb = (HostBatch*)p;
+  hb->b.gpos = gpos; hb->b.gvel = gvel; hb->b.cforce = cforce;
+}
+void ht_update_dynamic(void* p) {
+  HostBatch* hb = (HostBatch*)p;
+  for (int64_t w = 0; w < hb->b.W; ++w) world_update_dynamic(hb->dm, hb->b, w);
+}
+void ht_update_controllers(void* p, double dt) {
+  HostBatch* hb = (HostBatch*)p;
+  for (int64_t w = 0; w < hb->b.W; ++w) world_update_controllers(hb->dm, hb->b, w, dt);
+}
+void ht_update_constraints(void* p, double dt) {
+  HostBatch* hb = (HostBatch*)p;
+  for (int64_t w = 0; w < hb->b.W; ++w) world_update_constraints(hb->dm, hb->b, w, dt);
+}
+void ht_integrate(void* p, double dt) {
+  HostBatch* hb = (HostBatch*)p;
+  for (int64_t w = 0; w < hb->b.W; ++w) world_integrate(hb->dm, hb->b, w, dt);
+}
+// raw scratch access: which = index into the DevBatch double members in declaration order
+double* ht_array(void* p, const char* name) {
+  HostBatch* hb = (HostBatch*)p;
+  DevBatch& b = hb->b;
+  std::string s(name);
+  if (s == "pose") return b.pose; if (s == "twist") return b.twist; if (s == "J") return b.J;
+  if (s == "dJ") return b.dJ; if (s == "M") return b.M; if (s == "N") return b.N; if (s == "B") return b.B;
+  if (s == "Z") return b.Z; if (s == "Y") return b.Y; if (s == "gforce") return b.gforce;
+  if (s == "cjac") return b.cjac; if (s == "cvel") return b.cvel; if (s == "cA") return b.cA;
+  if (s == "caux") return b.caux;
+  return nullptr;
+}
+int* ht_iarray(void* p, const char* name) {
+  HostBatch* hb = (HostBatch*)p;
+  DevBatch& b = hb->b;
+  std::string s(name);
+  if (s == "cactive") return b.cactive; if (s == "cbranch") return b.cbranch; if (s == "cdol") return b.cdol;
+  if (s == "czidx") return b.czidx; if (s == "status") return b.status;
+  return nullptr;
+}
+void ht_pinv(int n, const double* a, double* out) {
+  if (n == 1) pinv_small<1>(a, out);
+  else if (n == 2) pinv_small<2>(a, out);
+  else if (n == 3) pinv_small<3>(a, out);
+  else pinv_small<4>(a, out);
+}
+int ht_eig6(const double* a, double* wr, double* wi) {
+  double tmp[36];
+  memcpy(tmp, a, sizeof(tmp));
+  return eig_real_general6(tmp, wr, wi) ? 1 : 0;
+}
+int ht_solve4(const double* a, const double* b, double* x) { return solve_small<4>(a, b, x) ? 1 : 0; }
+void ht_exp(const double* tw, double* out12) {
+  Se3 h;
+  se3_exp(tw, h);
+  se3_to12(h, out12);
+}
+}

@@ -1,0 +1,91 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes driver of the CPU build of the per-world
+routines (see arb_hosttest.cpp).  Mirrors the phase API on host numpy arrays with
+the device layouts ([elem][W])."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from arboris_b200 import _capi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SRC = os.path.join(HERE, "arb_hosttest.cpp")
+OUT = os.path.join(HERE, "_build", "libarb_hosttest.so")
+CSRC = os.path.join(ROOT, "arboris-python_b200", "csrc")
+
+
+def build():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
+    if os.path.isfile(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
+        return OUT
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off",
+                           "-Wno-unknown-pragmas", "-o", OUT, SRC])
+    return OUT
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        L.ht_create.restype = C.c_void_p
+        L.ht_create.argtypes = [C.POINTER(_capi.ModelDesc), C.c_int64, C.c_char_p, C.c_int]
+        L.ht_destroy.argtypes = [C.c_void_p]
+        L.ht_bind.argtypes = [C.c_void_p] * 4
+        for f in ("ht_update_dynamic",):
+            getattr(L, f).argtypes = [C.c_void_p]
+        for f in ("ht_update_controllers", "ht_update_constraints", "ht_integrate"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_double]
+        L.ht_array.restype = C.POINTER(C.c_double)
+        L.ht_array.argtypes = [C.c_void_p, C.c_char_p]
+        L.ht_iarray.restype = C.POINTER(C.c_int)
+        L.ht_iarray.argtypes = [C.c_void_p, C.c_char_p]
+        _lib = L
+    return _lib
+
+
+class HostBatch(object):
+    def __init__(self, model, W):
+        self.L = lib()
+        self.model, self.W = model, W
+        self.desc, self._keep = _capi.make_desc(model)
+        err = C.create_string_buffer(256)
+        self.h = self.L.ht_create(C.byref(self.desc), W, err, 256)
+        if not self.h:
+            raise RuntimeError(err.value.decode())
+        self.gpos = np.zeros((model.ngpos, W))
+        self.gvel = np.zeros((model.ndof, W))
+        self.cforce = np.zeros((max(model.nrows, 1), W))
+        self.L.ht_bind(self.h, self.gpos.ctypes.data, self.gvel.ctypes.data, self.cforce.ctypes.data)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.ht_destroy(self.h)
+            self.h = None
+
+    def update_dynamic(self):
+        self.L.ht_update_dynamic(self.h)
+
+    def update_controllers(self, dt):
+        self.L.ht_update_controllers(self.h, dt)
+
+    def update_constraints(self, dt):
+        self.L.ht_update_constraints(self.h, dt)
+
+    def integrate(self, dt):
+        self.L.ht_integrate(self.h, dt)
+
+    def arr(self, name, *shape):
+        p = self.L.ht_array(self.h, name.encode())
+        n = int(np.prod(shape))
+        return np.ctypeslib.as_array(p, shape=(n * self.W,)).reshape(shape + (self.W,))
+
+    def iarr(self, name, *shape):
+        p = self.L.ht_iarray(self.h, name.encode())
+        n = int(np.prod(shape))
+        return np.ctypeslib.as_array(p, shape=(n * self.W,)).reshape(shape + (self.W,))

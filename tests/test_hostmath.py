@@ -1,0 +1,128 @@
+"""CPU build (g++) of the very routines the CUDA kernels run per world
+(arboris-python_b200/csrc/arb_world.cuh and friends), checked against the
+real-reference trajectories and against numpy.linalg for the small dense kernels.
+No GPU needed; the GPU tests (-m gpu) repeat the trajectory checks through the
+C ABI on the device."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import load_golden
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "hosttest"))
+import harness  # noqa: E402
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)).max()/max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("name,tol", [("simplearm", 1e-12), ("human36_free", 1e-10),
+                                      ("ball_socket", 1e-12), ("simplearm_limits", 1e-12),
+                                      ("snake_loop", 1e-10), ("human36_contact", 1e-10)])
+def test_world_routines_vs_real_reference(name, tol):
+    """per step from identical states: M, N, Z, Y, forces, velocities <= tol relative;
+    active sets and solver branches bit-exact."""
+    model, tr = load_golden(name)
+    n, dt = model.ndof, float(tr["dt"])
+    W, T = tr["gpos"].shape[:2]
+    hb = harness.HostBatch(model, W)
+    gpos, gvel = tr["gpos_in"].T.copy(), tr["gvel_in"].T.copy()
+    cf = np.zeros((max(model.nrows, 1), W))
+    fs = list(tr["full_steps"])
+    flips, worst = 0, {}
+    for s in range(T):
+        hb.gpos[:], hb.gvel[:], hb.cforce[:] = gpos, gvel, cf
+        hb.update_dynamic()
+        hb.update_controllers(dt)
+        if s in fs:
+            i = fs.index(s)
+            for k, nm in (("mass", "M"), ("nleffects", "N"), ("impedance", "Z"), ("admittance", "Y")):
+                got = np.moveaxis(hb.arr(nm, n, n), -1, 0)
+                worst[k] = max(worst.get(k, 0), rel(got, tr[k][:, i]))
+        hb.update_constraints(dt)
+        if model.nc:
+            a = hb.iarr("cactive", model.nc).T
+            br = hb.iarr("cbranch", model.nc).T
+            flips += int((a != tr["active"][:, s]).sum()) + int((br*a != tr["branch"][:, s]).sum())
+            if name != "ball_socket":
+                worst["cforce"] = max(worst.get("cforce", 0),
+                                      rel(hb.cforce.T[:, :model.nrows], tr["cforce"][:, s]))
+        hb.integrate(dt)
+        worst["gvel"] = max(worst.get("gvel", 0), rel(hb.gvel.T, tr["gvel"][:, s]))
+        worst["gpos"] = max(worst.get("gpos", 0), rel(hb.gpos.T, tr["gpos"][:, s]))
+        gpos, gvel = tr["gpos"][:, s].T.copy(), tr["gvel"][:, s].T.copy()
+        if model.nrows:
+            cf = tr["cforce"][:, s].T.copy()
+    assert flips == 0
+    assert not hb.iarr("status").any()
+    for k, v in worst.items():
+        assert v <= tol, (k, v)
+
+
+def test_pinv_small_vs_numpy():
+    L = harness.lib()
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(0)
+    for n in (1, 2, 3, 4):
+        for trial in range(50):
+            a = rng.normal(size=(n, n))
+            full = True
+            if trial % 5 == 0 and n > 1:      # rank deficient
+                a[:, -1] = a[:, 0]*2.
+                full = False
+            if trial % 7 == 0:
+                a *= 1e-6
+            out = np.zeros((n, n))
+            L.ht_pinv(n, a.ctypes.data_as(dp), out.ctypes.data_as(dp))
+            ref = np.linalg.pinv(a)
+            assert rel(out, ref) < 1e-11*(np.linalg.cond(a) if full else 1e3), (n, trial)
+    z, out = np.zeros((4, 4)), np.ones((4, 4))
+    L.ht_pinv(4, z.ctypes.data_as(dp), out.ctypes.data_as(dp))
+    assert not out.any()
+
+
+def test_eig6_vs_numpy():
+    L = harness.lib()
+    rng = np.random.default_rng(1)
+    dp = C.POINTER(C.c_double)
+    for trial in range(300):
+        a = rng.normal(size=(6, 6))
+        if trial % 3 == 0:
+            a = a*np.logspace(-3, 3, 6)[None, :]
+        if trial % 4 == 0:   # shape of the sliding-friction matrix (constraints.py:815-821)
+            s = rng.normal(size=(3, 3))
+            s = s + s.T
+            a[:3, :3] = s + rng.normal()
+            a[3:, 3:] = s
+            a[:3, 3:] = -np.eye(3)*abs(rng.normal())
+            a[3:, :3] = np.eye(3)*rng.normal()
+        wr, wi = np.zeros(6), np.zeros(6)
+        ok = L.ht_eig6(a.ctypes.data_as(dp), wr.ctypes.data_as(dp), wi.ctypes.data_as(dp))
+        assert ok
+        ref = np.sort_complex(np.linalg.eigvals(a))
+        got = np.sort_complex(wr + 1j*wi)
+        assert np.abs(got - ref).max() < 1e-8*max(1., np.abs(ref).max()), (trial, got, ref)
+        assert (wi == 0).sum() == (ref.imag == 0).sum()
+
+
+def test_solve4_and_exp():
+    L = harness.lib()
+    dp = C.POINTER(C.c_double)
+    rng = np.random.default_rng(2)
+    L.ht_solve4.restype = C.c_int
+    for _ in range(50):
+        a, b, x = rng.normal(size=(4, 4)), rng.normal(size=4), np.zeros(4)
+        assert L.ht_solve4(a.ctypes.data_as(dp), b.ctypes.data_as(dp), x.ctypes.data_as(dp))
+        assert rel(x, np.linalg.solve(a, b)) < 1e-12*np.linalg.cond(a)
+    from oracle.arboris_oracle import twist_exp
+    for scale in (1., 1e-2, 1e-4, 0.):
+        tw = rng.normal(size=6)*np.array([scale]*3 + [1.]*3)
+        out = np.zeros(12)
+        L.ht_exp(tw.ctypes.data_as(dp), out.ctypes.data_as(dp))
+        H = twist_exp(tw)
+        assert np.abs(out[:9].reshape(3, 3) - H[:3, :3]).max() < 1e-14
+        assert np.abs(out[9:] - H[:3, 3]).max() < 1e-13*max(1., np.abs(H[:3, 3]).max())
