@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Benchmark of the batched Arboris step (BASELINE.json metric: world-steps/s,
+human36, fp64, dt = 1 ms).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (oracle port)
+
+A "step" is one pass of the hot path (update_dynamic -> update_controllers ->
+update_constraints -> integrate) over the whole batch of worlds.  Prints ONE JSON
+line (rank 0).  Under torchrun (N > 1) the worlds are sharded over the ranks with
+no data-path collective; NCCL only carries the timing/diagnostics reduction.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "arboris-python_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+DT = 1e-3
+# algorithmic flops per human36 world-step (1 FMA = 2 flop)
+FLOP_PER_WORLD_STEP = {"human36_contact": 0.99e6, "human36_free": 360118.}
+STATE_BYTES_PER_WORLD_STEP = 1504   # read+write of 94 doubles
+WORKLOADS = {
+    # BASELINE.json configs[4] (the configuration the metric's "1/2/4/8 B200" sweep is quoted on)
+    "human36_contact_262144": ("human36_contact", 262144),
+    # BASELINE.json configs[1]
+    "human36_free_4096": ("human36_free", 4096),
+    "human36_contact_16384": ("human36_contact", 16384),
+}
+RESET_EVERY = 250   # steps after which worlds are re-initialised (the uncontrolled humanoid
+                    # collapses and the reference's own sliding solve diverges after ~0.35 s)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="human36_contact_262144", choices=sorted(WORKLOADS))
+    ap.add_argument("--worlds", type=int, default=0, help="override the total number of worlds")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------
+# CPU baseline: the oracle port of the reference on the host cores (multiprocessing)
+# ---------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    scen, wid, seconds, warm = args
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[v] = "1"
+    from arboris_b200 import scenarios
+    from arboris_b200.flatten import flatten
+    from oracle.arboris_oracle import OracleWorld
+    model = flatten(scenarios.BUILDERS[scen]())
+    o = OracleWorld(model.to_dict())
+    o.gpos[:], o.gvel[:] = scenarios.initial_state(model, scen, wid)
+    # warm up past the free-fall so contacts are active like in the GPU run
+    for _ in range(warm):
+        o.step(DT)
+    n, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds and n < RESET_EVERY - warm:
+        o.step(DT)
+        n += 1
+    return n, time.perf_counter() - t0
+
+
+def cpu_baseline(scen, seconds):
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[v] = "1"
+    ctx = mp.get_context("spawn")
+    warm = 60 if scen == "human36_contact" else 5
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, [(scen, w, seconds, warm) for w in range(cores)])
+    steps = sum(r[0] for r in res)
+    wall = max(r[1] for r in res)
+    return {"value": steps/wall, "unit": "world-steps/s", "cores": cores, "kind": "port",
+            "sample": "%d worlds (one per core) x ~%d steps of %s after %d warm-up steps, "
+                      "numpy oracle port of the reference, BLAS threads = 1"
+                      % (cores, steps//max(cores, 1), scen, warm),
+            "per_core": steps/wall/cores}
+
+
+# ---------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        threading.Thread.__init__(self, daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True,
+                                     text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in self.rows)
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm)//2], "sm_max_mhz": float(self.rows[0][2]),
+                "power_w_max": max(float(r[3]) for r in self.rows), "samples": len(self.rows),
+                "reasons": sorted(reasons)}
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from arboris_b200 import scenarios, _capi
+    from arboris_b200.batch import BatchedWorld
+    from arboris_b200.flatten import flatten
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    scen, total = WORKLOADS[a.workload]
+    if a.worlds:
+        total = a.worlds
+    W = total // world_size                     # contiguous block of worlds per GPU
+    w0 = rank*W
+    model = flatten(scenarios.BUILDERS[scen]())
+    # synthetic seeded initial states; 4096 distinct worlds tiled over the shard
+    nseed = min(W, 4096)
+    gp, gv = scenarios.initial_states(model, scen, w0 % 4096, w0 % 4096 + nseed)
+    reps = (W + nseed - 1)//nseed
+    gp = np.tile(gp, (1, reps))[:, :W]
+    gv = np.tile(gv, (1, reps))[:, :W]
+    bw = BatchedWorld(model, W, device="cuda:%d" % local)
+    gpos0 = torch.as_tensor(gp, device=bw.device)
+    gvel0 = torch.as_tensor(gv, device=bw.device)
+
+    def reset():
+        bw.gpos.copy_(gpos0)
+        bw.gvel.copy_(gvel0)
+        bw.cforce.zero_()
+
+    def run_steps(k, done):
+        # k steps; worlds are re-initialised every RESET_EVERY steps (a device copy)
+        while k > 0:
+            if done % RESET_EVERY == 0:
+                reset()
+            c = min(k, RESET_EVERY - done % RESET_EVERY)
+            bw.step(DT, c)
+            k -= c
+            done += c
+        return done
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    warm = max(a.warmup, 3)
+    done = run_steps(warm, 0)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = bw.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    done = run_steps(a.steps, done)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = bw.launch_count() - l0
+    sampler.stop_flag = True
+    status = bw.status()
+    nbad = int((status & 1).ne(0).sum())
+    g, v, _ = bw.gpos, bw.gvel, None
+    nonfinite = int((~torch.isfinite(v)).any(0).sum())
+
+    # ---- end to end through the host-buffer entry point (arb_step_host) --------------------
+    e2e = None
+    if not a.no_e2e:
+        hg = torch.empty(gp.shape, dtype=torch.float64).pin_memory()
+        hv = torch.empty(gv.shape, dtype=torch.float64).pin_memory()
+        hf = torch.zeros((max(int(model.nrows), 1), W), dtype=torch.float64).pin_memory()
+        hg.copy_(torch.as_tensor(gp)); hv.copy_(torch.as_tensor(gv))
+        hgn, hvn, hfn = hg.numpy(), hv.numpy(), hf.numpy()
+        k_e2e = max(3, min(a.steps, 20))
+        for _ in range(3):
+            bw.step_host(hgn, hvn, hfn, DT, 1)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            bw.step_host(hgn, hvn, hfn, DT, 1)    # H2D state, 1 step, D2H state, sync
+        torch.cuda.synchronize()
+        t_e2e = time.perf_counter() - t0
+        bytes_in = (hgn.nbytes + hvn.nbytes + (hfn.nbytes if model.nrows else 0))
+        e2e = [t_e2e/k_e2e, bytes_in, bytes_in, k_e2e]
+
+    # max over ranks of the timed region; totals over ranks
+    t = torch.tensor([ms, e2e[0]*1e3 if e2e else 0.], device=bw.device, dtype=torch.float64)
+    cnt = torch.tensor([float(nonfinite), float(launches)], device=bw.device, dtype=torch.float64)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_all, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world_size > 1:
+            dist.destroy_process_group()
+        return
+    total_worlds = W*world_size
+    value = total_worlds*a.steps/(ms_all*1e-3)
+    lib = _capi.load()
+    peak = C_double()
+    lib.arb_measure_fp64_peak(local, peak.ref())
+    fp64_peak = peak.value
+    flop = FLOP_PER_WORLD_STEP[scen]
+    achieved = (value/world_size)*flop        # per GPU, flop/s
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.))
+    out = {
+        "metric": "world-steps/s (human36, fp64, dt=1ms)", "value": value, "unit": "world-steps/s",
+        "n_gpus": world_size, "steps": a.steps, "warmup": warm, "ms_per_step": ms_all/a.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (seeded random initial states, SURVEY.md 8(d))",
+        "config": {"workload": a.workload, "scenario": scen, "worlds_total": total_worlds,
+                   "worlds_per_gpu": W, "dt": DT, "constraints": int(model.nc),
+                   "reset_every_steps": RESET_EVERY,
+                   "l2": "state of all worlds (%.0f MB) and per-world scratch exceed L2; no flush needed"
+                         % (total_worlds/world_size*STATE_BYTES_PER_WORLD_STEP/2/1e6),
+                   "parallelism": "worlds sharded over %d GPU(s), no collective on the step path" % world_size},
+        "gpu_launches": int(cnt[1]),
+        "nonfinite_worlds": int(cnt[0]),
+        "roofline": {"bound": "fp64", "achieved": achieved/1e12, "peak": fp64_peak/1e12,
+                     "unit": "TFLOP/s", "frac": achieved/fp64_peak if fp64_peak else None,
+                     "traffic": None,
+                     "peak_source": "DFMA micro-benchmark measured in this run (arb_measure_fp64_peak); "
+                                    "MEASURED_PEAKS.json has no fp64 entry",
+                     "flop_per_world_step": flop,
+                     "hbm": {"achieved": value/world_size*STATE_BYTES_PER_WORLD_STEP/1e9,
+                             "peak": hbm_peak, "unit": "GB/s",
+                             "frac": value/world_size*STATE_BYTES_PER_WORLD_STEP/1e9/hbm_peak}},
+        "clocks": sampler.summary(),
+    }
+    if e2e:
+        out["e2e"] = {"value": total_worlds/(e2e_ms*1e-3), "unit": "world-steps/s",
+                      "h2d_bytes_per_step": e2e[1]*world_size, "d2h_bytes_per_step": e2e[2]*world_size,
+                      "steps": e2e[3], "how": "arb_step_host: pinned host state -> device, 1 step, "
+                                              "device -> host, synchronised, every step"}
+    if not a.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(scen, a.cpu_seconds)
+    print(json.dumps(out))
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+class C_double(object):
+    def __init__(self):
+        import ctypes
+        self._c = ctypes.c_double(0.)
+        self._ct = ctypes
+
+    def ref(self):
+        return self._ct.byref(self._c)
+
+    value = property(lambda self: self._c.value)
+
+
+def run_reference(a):
+    """Reference arm: the reference's CPU implementation of the path (the numpy oracle
+    port -- the Python reference cannot travel to the GPU box) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scen, total = WORKLOADS[a.workload]
+    base = cpu_baseline(scen, a.cpu_seconds)
+    v = base["value"]
+    out = {
+        "impl": "reference", "metric": "world-steps/s (human36, fp64, dt=1ms)", "value": v,
+        "unit": "world-steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3/v if v else None, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic (seeded random initial states)",
+        "config": {"workload": a.workload, "scenario": scen, "worlds_total": total, "dt": DT},
+        "cpu_baseline": base,
+        "e2e": {"value": v, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
