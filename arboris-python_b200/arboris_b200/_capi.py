@@ -80,6 +80,7 @@ SYMBOLS = [
     ("arb_batch_create", _i32, [_vp, _i64, _i32, _vp, C.POINTER(_vp)]),
     ("arb_batch_destroy", None, [_vp]),
     ("arb_batch_set_stream", _i32, [_vp, _vp]),
+    ("arb_batch_set_option", _i32, [_vp, C.c_char_p, _i32]),
     ("arb_batch_bind_state", _i32, [_vp, _vp, _vp, _vp]),
     ("arb_update_dynamic", _i32, [_vp]),
     ("arb_update_controllers", _i32, [_vp, _dbl]),

@@ -73,6 +73,11 @@ class BatchedWorld(object):
         s = torch.cuda.current_stream(self.device) if self._stream is None else self._stream
         self._lib.arb_batch_set_stream(self._batch_h, C.c_void_p(s.cuda_stream))
 
+    def set_option(self, name, value):
+        """``force_phases`` / ``prepare_warp`` switches of ``arb_batch_set_option``."""
+        _capi.check(self._lib, self._lib.arb_batch_set_option(
+            self._batch_h, name.encode(), int(value)))
+
     def close(self):
         if getattr(self, "_batch_h", None):
             self._lib.arb_batch_destroy(self._batch_h)

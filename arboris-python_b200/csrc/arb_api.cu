@@ -62,6 +62,10 @@ static int model_to_device(arb_model* mo, int device) {
   rc |= upload(h.crow, &m.crow, own);     rc |= upload(h.cdbl, &m.cdbl, own);
   rc |= upload(h.atype, &m.atype, own);   rc |= upload(h.aint, &m.aint, own);
   rc |= upload(h.adbl, &m.adbl, own);     rc |= upload(h.ablob, &m.ablob, own);
+  rc |= upload(h.dofbody, &m.dofbody, own); rc |= upload(h.dofpos, &m.dofpos, own);
+  rc |= upload(h.gen_body, &m.gen_body, own);
+  rc |= upload(h.cgen1, &m.cgen1, own);   rc |= upload(h.cgen0, &m.cgen0, own);
+  m.ngen = h.ngen; m.ngrows = h.ngrows;
   if (rc) return -100;
   for (int i = 0; i < 3; ++i) m.up[i] = h.up[i];
   mo->dev[device] = m;
@@ -121,7 +125,7 @@ extern "C" int arb_batch_create(const arb_model* model, int64_t nworlds, int dev
 
 // The API-shaped phases keep every intermediate in HBM; that scratch (about
 // 114 KB per human36 world) is only allocated when a phase call needs it.
-static int ensure_phase_scratch(arb_batch* b) {
+int arb_ensure_phase_scratch(arb_batch* b) {
   if (b->scratch_dbl) return 0;
   CUDA_OK(cudaSetDevice(b->device));
   ScratchSizes s = scratch_sizes(b->model->host);
@@ -147,6 +151,15 @@ extern "C" void arb_batch_destroy(arb_batch* b) {
 extern "C" int arb_batch_set_stream(arb_batch* b, void* stream) {
   if (!b) { arb_set_error("null batch"); return -1; }
   b->stream = (cudaStream_t)stream;
+  return 0;
+}
+
+extern "C" int arb_batch_set_option(arb_batch* b, const char* name, int value) {
+  if (!b || !name) { arb_set_error("null argument"); return -1; }
+  const std::string s(name);
+  if (s == "force_phases") b->force_phases = value;
+  else if (s == "prepare_warp") b->prepare_warp = value;
+  else { arb_set_error("unknown option " + s); return -1; }
   return 0;
 }
 
@@ -200,7 +213,7 @@ static inline unsigned lpw_grid(int64_t W) { return (unsigned)((W + LPW_THREADS 
 extern "C" int arb_update_dynamic(arb_batch* b) {
   int rc = check_bound(b); if (rc) return rc;
   CUDA_OK(cudaSetDevice(b->device));
-  rc = ensure_phase_scratch(b); if (rc) return rc;
+  rc = arb_ensure_phase_scratch(b); if (rc) return rc;
   k_update_dynamic<<<lpw_grid(b->d.W), LPW_THREADS, 0, b->stream>>>(b->m, b->d);
   LAUNCH_CHECK(b);
   return 0;
@@ -209,7 +222,7 @@ extern "C" int arb_update_controllers(arb_batch* b, double dt) {
   int rc = check_bound(b); if (rc) return rc;
   if (!(dt > 0)) { arb_set_error("dt must be > 0"); return -3; }
   CUDA_OK(cudaSetDevice(b->device));
-  rc = ensure_phase_scratch(b); if (rc) return rc;
+  rc = arb_ensure_phase_scratch(b); if (rc) return rc;
   k_update_controllers<<<lpw_grid(b->d.W), LPW_THREADS, 0, b->stream>>>(b->m, b->d, dt);
   LAUNCH_CHECK(b);
   return 0;
@@ -218,7 +231,7 @@ extern "C" int arb_update_constraints(arb_batch* b, double dt) {
   int rc = check_bound(b); if (rc) return rc;
   if (!(dt > 0)) { arb_set_error("dt must be > 0"); return -3; }
   CUDA_OK(cudaSetDevice(b->device));
-  rc = ensure_phase_scratch(b); if (rc) return rc;
+  rc = arb_ensure_phase_scratch(b); if (rc) return rc;
   k_update_constraints<<<lpw_grid(b->d.W), LPW_THREADS, 0, b->stream>>>(b->m, b->d, dt);
   LAUNCH_CHECK(b);
   return 0;
@@ -227,7 +240,7 @@ extern "C" int arb_integrate(arb_batch* b, double dt) {
   int rc = check_bound(b); if (rc) return rc;
   if (!(dt > 0)) { arb_set_error("dt must be > 0"); return -3; }
   CUDA_OK(cudaSetDevice(b->device));
-  rc = ensure_phase_scratch(b); if (rc) return rc;
+  rc = arb_ensure_phase_scratch(b); if (rc) return rc;
   k_integrate<<<lpw_grid(b->d.W), LPW_THREADS, 0, b->stream>>>(b->m, b->d, dt);
   LAUNCH_CHECK(b);
   return 0;
@@ -236,7 +249,7 @@ extern "C" int arb_integrate(arb_batch* b, double dt) {
 // nsteps of the simulate() loop through the four phase kernels (used when the
 // fused warp-per-world kernel does not support the model, and by tests).
 int arb_step_phases(arb_batch* b, const double* dts, int nsteps) {
-  int rc = ensure_phase_scratch(b); if (rc) return rc;
+  int rc = arb_ensure_phase_scratch(b); if (rc) return rc;
   const unsigned g = lpw_grid(b->d.W);
   for (int s = 0; s < nsteps; ++s) {
     const double dt = dts[s];

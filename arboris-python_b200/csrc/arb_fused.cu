@@ -1,7 +1,84 @@
-// Fused warp-per-world step -- placeholder until the kernel lands: reports
-// "unsupported" so arb_step runs the four lane-per-world phase kernels.
+// Fused step driver: prepare -> gs -> finish per time step (see arb_fused.cuh).
+// prepare runs warp-per-world (arb_prepare_warp.cuh) when the model fits that kernel's
+// limits, else lane-per-world; gs and finish are lane-per-world.
+#include <cuda_runtime.h>
+#include <string>
+
+#include "arb_fused.cuh"
 #include "arb_internal.h"
 
-bool arb_fused_supported(const arb_batch*) { return false; }
-int arb_fused_step(arb_batch* b, const double* dts, int nsteps) { return arb_step_phases(b, dts, nsteps); }
-void arb_fused_release(arb_batch*) {}
+struct FusedState {
+  double* dbl = nullptr;
+  int* ints = nullptr;
+};
+
+#define CUDA_OKF(call)                                                            \
+  do {                                                                            \
+    cudaError_t e_ = (call);                                                      \
+    if (e_ != cudaSuccess) {                                                      \
+      arb_set_error(std::string(#call) + ": " + cudaGetErrorString(e_));          \
+      return -100;                                                                \
+    }                                                                             \
+  } while (0)
+
+#define FUSED_THREADS 64
+
+__global__ void __launch_bounds__(FUSED_THREADS) k_fused_prepare_lane(DevModel m, DevBatch b, double dt) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= b.W) return;
+  world_update_dynamic(m, b, w);
+  world_fused_prepare(m, b, w, dt);
+}
+__global__ void __launch_bounds__(FUSED_THREADS) k_fused_gs(DevModel m, DevBatch b, double dt) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < b.W) world_fused_gs(m, b, w, dt);
+}
+__global__ void __launch_bounds__(FUSED_THREADS) k_fused_finish(DevModel m, DevBatch b, double dt) {
+  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w < b.W) world_fused_finish(m, b, w, dt);
+}
+
+bool arb_fused_supported(const arb_batch*) { return true; }
+
+static int ensure_fused_scratch(arb_batch* b) {
+  if (b->fused) return 0;
+  FusedSizes s = fused_sizes(b->model->host);
+  const int64_t W = b->d.W;
+  FusedState* f = new FusedState();
+  CUDA_OKF(cudaMalloc((void**)&f->dbl, sizeof(double) * s.total_doubles() * W));
+  CUDA_OKF(cudaMalloc((void**)&f->ints, sizeof(int) * s.total_ints() * W));
+  CUDA_OKF(cudaMemsetAsync(f->dbl, 0, sizeof(double) * s.total_doubles() * W, b->stream));
+  CUDA_OKF(cudaMemsetAsync(f->ints, 0, sizeof(int) * s.total_ints() * W, b->stream));
+  carve_fused(s, W, f->dbl, f->ints, b->d);
+  b->fused = f;
+  return 0;
+}
+
+
+
+int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
+  int rc = ensure_fused_scratch(b);
+  if (rc) return rc;
+  rc = arb_ensure_phase_scratch(b);
+  if (rc) return rc;
+  const unsigned g = (unsigned)((b->d.W + FUSED_THREADS - 1) / FUSED_THREADS);
+  for (int s = 0; s < nsteps; ++s) {
+    const double dt = dts[s];
+    if (!(dt > 0)) { arb_set_error("dt must be > 0"); return -3; }
+    k_fused_prepare_lane<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    if (b->m.nc > 0) k_fused_gs<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    k_fused_finish<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    b->launches += (b->m.nc > 0) ? 3 : 2;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { arb_set_error(std::string("kernel launch: ") + cudaGetErrorString(e)); return -101; }
+  return 0;
+}
+
+void arb_fused_release(arb_batch* b) {
+  if (!b->fused) return;
+  cudaFree(b->fused->dbl);
+  cudaFree(b->fused->ints);
+  delete b->fused;
+  b->fused = nullptr;
+}

@@ -1,0 +1,480 @@
+// The fused step, stage by stage.  Same results as the four API phases
+// (core.py:1356-1363) but organised for the GPU:
+//
+//  prepare : kinematics, assembly of Z = M/dt + B + N, gravity/controllers, then instead
+//            of the explicit 42x42 inverse (core.py:818) a no-fill elimination of Z that
+//            exploits the tree sparsity (Z[i][j] != 0 only for dofs on a common root path;
+//            eliminating dofs leaf-to-root creates no fill-in), the unconstrained velocity
+//            q_free = Z^-1 (M q'/dt + g), and the constraint problem reduced to "generator"
+//            space: constraint Jacobians are J_c = T1_c J_body1 - T0_c J_body0, so with
+//            G = stacked body Jacobians of the few bodies that carry constraint frames
+//            (the two feet for human36) only  W = Z^-1 G^T,  Lambda = G W  and v0 = G q_free
+//            are needed:  J_c Y J_d^T = T_c Lambda T_d^T  (core.py:925-927).
+//  gs      : the 20 sequential Gauss-Seidel sweeps (core.py:929-935) in generator space,
+//            one world per lane; u = v0 + Lambda y is kept up to date, y = sum T_c^T f_c.
+//  finish  : q'+ = q_free + W y (equals core.py:975-976) and joint integration.
+//
+// The scalar (lane-per-world) prepare below is the portable implementation and the
+// reference for the warp-per-world kernel in arb_fused.cu; gs and finish are always
+// lane-per-world.
+#pragma once
+#include "arb_constraints.cuh"
+#include "arb_world.cuh"
+
+// ---- no-fill elimination of Z in place (row-major n x n, only structural entries touched)
+// after it: Z[k][k] pivots, Z[anc][k] multipliers (column k above the diagonal, already
+// divided by the pivot), Z[k][anc] the eliminated row.
+ARB_D bool tree_factor(const DevModel& m, double* Z, int64_t W, int64_t w) {
+  const int n = m.ndof;
+  bool ok = true;
+  for (int k = n - 1; k >= 0; --k) {
+    const int a = m.dofpos[k];
+    const int* anc = m.pathdof + m.coloff[m.dofbody[k]];
+    const double d = AT(Z, k * n + k);
+    if (!(fabs(d) > 0.)) ok = false;
+    const double inv = 1. / d;
+    for (int i = 0; i < a; ++i) {
+      const int ai = anc[i];
+      const double l = AT(Z, ai * n + k) * inv;
+      AT(Z, ai * n + k) = l;
+      for (int j = 0; j < a; ++j) AT(Z, ai * n + anc[j]) -= l * AT(Z, k * n + anc[j]);
+    }
+  }
+  return ok;
+}
+// x <- Z^-1 x using the factorisation above
+ARB_D void tree_solve(const DevModel& m, const double* Z, double* x, int64_t W, int64_t w) {
+  const int n = m.ndof;
+  for (int k = n - 1; k >= 0; --k) {
+    const int a = m.dofpos[k];
+    const int* anc = m.pathdof + m.coloff[m.dofbody[k]];
+    const double rk = AT(x, k);
+    if (rk == 0.) continue;
+    for (int i = 0; i < a; ++i) AT(x, anc[i]) -= AT(Z, anc[i] * n + k) * rk;
+  }
+  for (int k = 0; k < n; ++k) {
+    const int a = m.dofpos[k];
+    const int* anc = m.pathdof + m.coloff[m.dofbody[k]];
+    double t = AT(x, k);
+    for (int j = 0; j < a; ++j) t -= AT(Z, k * n + anc[j]) * AT(x, anc[j]);
+    AT(x, k) = t / AT(Z, k * n + k);
+  }
+}
+
+// Per-constraint update from body poses/twists: activation, aux (sdist / pos0 / q) and the
+// maps T1 (from body1's twist) and T0 (from body0's twist) to the constraint rows.
+// Returns the active flag.  pose/twist accessors go through P (12 doubles) and TW (6).
+ARB_D bool constraint_update(const DevModel& m, int c, const Se3& P0, const Se3& P1, const double* TW0,
+                             const double* TW1, double q, double dt, double* aux, double* T1,
+                             double* T0, int* zidx) {
+  const int type = m.ctype[c];
+  const double* cd = m.cdbl + ARB_CONS_NDBL * c;
+  if (type == ARB_CONS_JOINT_LIMITS) {
+    aux[0] = q;
+    return (q - cd[0] < cd[2]) || (cd[1] - q < cd[2]);
+  }
+  Se3 bp0, bp1;
+  se3_from16(cd, bp0);
+  se3_from16(cd + 16, bp1);
+  Se3 cb0, cb1;  // frames on the two bodies between which the constraint acts
+  int r0, nr;
+  bool active;
+  if (type == ARB_CONS_BALL_SOCKET) {
+    cb0 = bp0; cb1 = bp1; r0 = 3; nr = 3; active = true;
+  } else {
+    Se3 Hg0, Hgp, Hg0i;
+    const double* coef = cd + 32;
+    se3_mul(P0, bp0, Hg0);
+    se3_mul(P1, bp1, Hgp);
+    se3_inv(Hg0, Hg0i);
+    double p01[3], t3[3];
+    m3_mulv(Hg0i.R, Hgp.p, t3);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p01[i] = t3[i] + Hg0i.p[i];
+    const double csdist = (coef[0] * p01[0] + coef[1] * p01[1] + coef[2] * p01[2]) - coef[3];
+    Se3 Hc0, Hc1, P0i, P1i, Hc0i, Hc0c1;
+    zaligned(coef, Hc0.R, zidx);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Hc1.R[i] = Hc0.R[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { Hc0.p[i] = p01[i] - csdist * coef[i]; Hc1.p[i] = p01[i]; }
+    se3_inv(P0, P0i);
+    se3_inv(P1, P1i);
+    se3_mul(P0i, Hc0, cb0);
+    se3_mul(P1i, Hc1, cb1);
+    double f0t[6], f1t[6], y[6];
+    iad_apply(cb0, TW0, f0t);
+    iad_apply(cb1, TW1, f1t);
+    se3_inv(Hc0, Hc0i);
+    se3_mul(Hc0i, Hc1, Hc0c1);
+    ad_apply(Hc0c1, f1t, y);
+    const double dsdist = y[5] - f0t[5];
+    active = (csdist + dsdist * dt < cd[40]);
+    aux[0] = csdist;
+    r0 = 2; nr = 4;
+    if (!active) return false;
+  }
+  // H_01 = inv(pose0 cb0) (pose1 cb1);  T1 = (Ad(H_01) Ad(cb1^-1))[rows], T0 = Ad(cb0^-1)[rows]
+  Se3 F0, F1, F0i, H01;
+  se3_mul(P0, cb0, F0);
+  se3_mul(P1, cb1, F1);
+  se3_inv(F0, F0i);
+  se3_mul(F0i, F1, H01);
+  if (type == ARB_CONS_BALL_SOCKET) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) aux[i] = H01.p[i];
+  }
+#pragma unroll
+  for (int col = 0; col < 6; ++col) {
+    double e[6] = {0., 0., 0., 0., 0., 0.}, y[6], z[6];
+    e[col] = 1.;
+    iad_apply(cb1, e, y);
+    ad_apply(H01, y, z);
+    for (int r = 0; r < nr; ++r) T1[r * 6 + col] = z[r0 + r];
+    iad_apply(cb0, e, y);
+    for (int r = 0; r < nr; ++r) T0[r * 6 + col] = y[r0 + r];
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------
+// prepare, scalar version: runs after world_update_dynamic (uses its scratch).
+ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, double dt) {
+  const int64_t W = b.W;
+  const int n = m.ndof, NG = m.ngrows;
+  // controllers: gforce and Z (no inverse)                                 (core.py:812-817)
+  for (int i = 0; i < n; ++i) AT(b.gforce, i) = 0.;
+  for (int i = 0; i < n * n; ++i) AT(b.Z, i) = AT(b.M, i) / dt + AT(b.B, i) + AT(b.N, i);
+  for (int a = 0; a < m.na; ++a) {
+    if (m.atype[a] == ARB_CTRL_WEIGHT) {
+      const double grav = m.adbl[4 * a];
+      double gt[6] = {0., 0., 0., grav * m.up[0], grav * m.up[1], grav * m.up[2]};
+      for (int j = 0; j < m.nj; ++j) {
+        if (!(m.bflags[j] & ARB_BODY_MASSIVE)) continue;
+        Se3 H;
+        load_pose(b, j + 1, w, H);
+        double g[6], wr[6];
+        iad_apply(H, gt, g);
+        const double* Mb = m.bmass + 36 * j;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          double t = 0.;
+#pragma unroll
+          for (int c = 0; c < 6; ++c) t += Mb[6 * r + c] * g[c];
+          wr[r] = t;
+        }
+        const int off = m.coloff[j + 1], kc = m.kcols[j + 1];
+        for (int l = 0; l < kc; ++l) {
+          double t = 0.;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) t += AT(b.J, (off + l) * 6 + i) * wr[i];
+          AT(b.gforce, m.pathdof[off + l]) += t;
+        }
+      }
+    } else {
+      const int mm = m.aint[4 * a], off = m.aint[4 * a + 1];
+      const double* dofs = m.ablob + off;
+      const double* gmap = dofs + mm;
+      const double* kp = gmap + mm;
+      const double* kd = kp + mm * mm;
+      const double* qd = kd + mm * mm;
+      const double* dqd = qd + mm;
+      for (int i = 0; i < mm; ++i) {
+        double t = 0., t2 = 0.;
+        for (int j = 0; j < mm; ++j) t += kp[i * mm + j] * (qd[j] - AT(b.gpos, (int)gmap[j]));
+        for (int j = 0; j < mm; ++j) t2 += kd[i * mm + j] * dqd[j];
+        AT(b.gforce, (int)dofs[i]) += t + t2;
+        for (int j = 0; j < mm; ++j)
+          AT(b.Z, (int)dofs[i] * n + (int)dofs[j]) -= -(dt * kp[i * mm + j] + kd[i * mm + j]);
+      }
+    }
+  }
+  // rhs = M gvel/dt + gforce ; q_free = Z^-1 rhs
+  for (int i = 0; i < n; ++i) {
+    double t = 0.;
+    for (int j = 0; j < n; ++j) t += AT(b.M, i * n + j) * (AT(b.gvel, j) / dt);
+    AT(b.fq, i) = t + AT(b.gforce, i);
+  }
+  if (!tree_factor(m, b.Z, W, w)) b.status[w] |= ARB_STATUS_SINGULAR;
+  tree_solve(m, b.Z, b.fq, W, w);
+  // constraints: activation, T maps
+  bool any = false;
+  for (int c = 0; c < m.nc; ++c) {
+    const int* ci = m.cint + ARB_CONS_NINT * c;
+    const int type = m.ctype[c];
+    const int r0 = m.crow[c];
+    AT(b.factive, c) = 0;
+    AT(b.fbranch, c) = 0;
+    if (!ci[3]) continue;
+    double aux[4] = {0., 0., 0., 0.}, T1[24], T0[24];
+    int zi[3] = {0, 0, 0};
+    bool act;
+    if (type == ARB_CONS_JOINT_LIMITS) {
+      Se3 I;
+      se3_identity(I);
+      act = constraint_update(m, c, I, I, nullptr, nullptr, AT(b.gpos, ci[2]), dt, aux, T1, T0, zi);
+      AT(b.cforce, r0) = 0.;
+    } else {
+      Se3 P0, P1;
+      double TW0[6], TW1[6];
+      load_pose(b, ci[0], w, P0);
+      load_pose(b, ci[1], w, P1);
+      load_twist(b, ci[0], w, TW0);
+      load_twist(b, ci[1], w, TW1);
+      act = constraint_update(m, c, P0, P1, TW0, TW1, 0., dt, aux, T1, T0, zi);
+      if (type == ARB_CONS_SOFT_FINGER_PLANE_POINT) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) AT(b.cforce, r0 + i) = 0.;
+      }
+      if (act) {
+        const int nr = arb_cons_ndol(type);
+        for (int i = 0; i < nr * 6; ++i) { AT(b.fT1, c * 24 + i) = T1[i]; AT(b.fT0, c * 24 + i) = T0[i]; }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) AT(b.faux, 4 * c + i) = aux[i];
+    AT(b.factive, c) = act ? 1 : 0;
+    any = any || act;
+  }
+  if (!any) return;
+  // generator space: W = Z^-1 G^T, Lambda = G W, v0 = G q_free
+  for (int g = 0; g < NG; ++g) {
+    double* x = b.fW + (int64_t)g * n * W;
+    for (int i = 0; i < n; ++i) AT(x, i) = 0.;
+    if (g < 6 * m.ngen) {
+      const int body = m.gen_body[g / 6], r = g % 6;
+      const int off = m.coloff[body], kc = m.kcols[body];
+      for (int l = 0; l < kc; ++l) AT(x, m.pathdof[off + l]) = AT(b.J, (off + l) * 6 + r);
+    } else {
+      for (int c = 0; c < m.nc; ++c)
+        if (m.ctype[c] == ARB_CONS_JOINT_LIMITS && m.cgen1[c] == g) AT(x, m.cint[ARB_CONS_NINT * c + 1]) = 1.;
+    }
+    tree_solve(m, b.Z, x, W, w);
+  }
+  for (int g = 0; g < NG; ++g) {
+    // row g of G applied to a dof-vector
+    for (int h = 0; h <= NG; ++h) {
+      const double* x = (h < NG) ? b.fW + (int64_t)h * n * W : b.fq;
+      double t = 0.;
+      if (g < 6 * m.ngen) {
+        const int body = m.gen_body[g / 6], r = g % 6;
+        const int off = m.coloff[body], kc = m.kcols[body];
+        for (int l = 0; l < kc; ++l) t += AT(b.J, (off + l) * 6 + r) * AT(x, m.pathdof[off + l]);
+      } else {
+        for (int c = 0; c < m.nc; ++c)
+          if (m.ctype[c] == ARB_CONS_JOINT_LIMITS && m.cgen1[c] == g) t = AT(x, m.cint[ARB_CONS_NINT * c + 1]);
+      }
+      if (h < NG) AT(b.fLam, g * NG + h) = t; else AT(b.fv0, g) = t;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Gauss-Seidel in generator space, one world per lane.
+ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, double dt) {
+  const int64_t W = b.W;
+  const int NG = m.ngrows;
+  int status = 0;
+  bool any = false;
+  for (int c = 0; c < m.nc; ++c) any = any || AT(b.factive, c);
+  for (int g = 0; g < NG; ++g) AT(b.fy, g) = 0.;
+  if (!any) return;
+  // y0 = sum T_c^T f_c (warm start of ball-and-socket forces), diagonal blocks and pinv
+  for (int c = 0; c < m.nc; ++c) {
+    if (!AT(b.factive, c)) continue;
+    const int type = m.ctype[c];
+    const int nd = arb_cons_ndol(type);
+    const int r0 = m.crow[c];
+    const int g1 = m.cgen1[c], g0 = m.cgen0[c];
+    if (type == ARB_CONS_JOINT_LIMITS) {
+      const double a = AT(b.fLam, g1 * NG + g1);
+      double p;
+      pinv_small<1>(&a, &p);
+      AT(b.fAcc, r0 * 4) = a;
+      AT(b.fP, r0 * 4) = p;
+      AT(b.fy, g1) += AT(b.cforce, r0);
+      continue;
+    }
+    // A_cc = sum over sides s,t of  sign * T_s Lambda[g_s, g_t] T_t^T
+    double A[16];
+    for (int i = 0; i < nd * nd; ++i) A[i] = 0.;
+    for (int s = 0; s < 2; ++s) {
+      const int gs = s ? g0 : g1;
+      if (gs < 0) continue;
+      const double* Ts = s ? b.fT0 : b.fT1;
+      for (int t = 0; t < 2; ++t) {
+        const int gt = t ? g0 : g1;
+        if (gt < 0) continue;
+        const double* Tt = t ? b.fT0 : b.fT1;
+        const double sign = (s == t) ? 1. : -1.;
+        for (int i = 0; i < nd; ++i) {
+          double tl[6];  // row i of T_s Lambda[gs.., gt..]
+#pragma unroll
+          for (int q = 0; q < 6; ++q) {
+            double acc = 0.;
+#pragma unroll
+            for (int p = 0; p < 6; ++p) acc += AT(Ts, c * 24 + i * 6 + p) * AT(b.fLam, (gs + p) * NG + gt + q);
+            tl[q] = acc;
+          }
+          for (int j = 0; j < nd; ++j) {
+            double acc = 0.;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) acc += tl[q] * AT(Tt, c * 24 + j * 6 + q);
+            A[i * nd + j] += sign * acc;
+          }
+        }
+      }
+    }
+    double P[16];
+    if (nd == 3) pinv_small<3>(A, P); else pinv_small<4>(A, P);
+    for (int i = 0; i < nd * nd; ++i) { AT(b.fAcc, r0 * 4 + i) = A[i]; AT(b.fP, r0 * 4 + i) = P[i]; }
+    for (int s = 0; s < 2; ++s) {
+      const int gs = s ? g0 : g1;
+      if (gs < 0) continue;
+      const double* Ts = s ? b.fT0 : b.fT1;
+      const double sign = s ? -1. : 1.;
+#pragma unroll
+      for (int p = 0; p < 6; ++p) {
+        double acc = 0.;
+        for (int i = 0; i < nd; ++i) acc += AT(Ts, c * 24 + i * 6 + p) * AT(b.cforce, r0 + i);
+        AT(b.fy, gs + p) += sign * acc;
+      }
+    }
+  }
+  // u = v0 + Lambda y0
+  for (int g = 0; g < NG; ++g) {
+    double t = AT(b.fv0, g);
+    for (int h = 0; h < NG; ++h) {
+      const double yh = AT(b.fy, h);
+      if (yh != 0.) t += AT(b.fLam, g * NG + h) * yh;
+    }
+    AT(b.fu, g) = t;
+  }
+  for (int sweep = 0; sweep < ARB_GS_SWEEPS; ++sweep) {
+    for (int c = 0; c < m.nc; ++c) {
+      if (!AT(b.factive, c)) continue;
+      const int type = m.ctype[c];
+      const double* cd = m.cdbl + ARB_CONS_NDBL * c;
+      const int r0 = m.crow[c];
+      const int g1 = m.cgen1[c], g0 = m.cgen0[c];
+      if (type == ARB_CONS_JOINT_LIMITS) {
+        const double a = AT(b.fAcc, r0 * 4), p = AT(b.fP, r0 * 4);
+        const double f = AT(b.cforce, r0), v = AT(b.fu, g1), q = AT(b.faux, 4 * c);
+        const double pred = q + dt * (v - a * f);
+        double nf;
+        int br;
+        if (pred <= cd[0]) { nf = p * ((cd[0] - pred) / dt); br = 2; }
+        else if (cd[1] <= pred) { nf = p * ((cd[1] - pred) / dt); br = 3; }
+        else { nf = 0.; br = 1; }
+        const double df = nf - f;
+        AT(b.cforce, r0) = nf;
+        AT(b.fbranch, c) = br;
+        if (df != 0.) {
+          AT(b.fy, g1) += df;
+          for (int g = 0; g < NG; ++g) AT(b.fu, g) += AT(b.fLam, g * NG + g1) * df;
+        }
+        continue;
+      }
+      const int nd = arb_cons_ndol(type);
+      // constraint velocity from the generator velocities
+      double v[4], f[4], df[4];
+      for (int i = 0; i < nd; ++i) {
+        double acc = 0.;
+        if (g1 >= 0)
+#pragma unroll
+          for (int p = 0; p < 6; ++p) acc += AT(b.fT1, c * 24 + i * 6 + p) * AT(b.fu, g1 + p);
+        if (g0 >= 0)
+#pragma unroll
+          for (int p = 0; p < 6; ++p) acc -= AT(b.fT0, c * 24 + i * 6 + p) * AT(b.fu, g0 + p);
+        v[i] = acc;
+        f[i] = AT(b.cforce, r0 + i);
+      }
+      if (type == ARB_CONS_BALL_SOCKET) {
+        double rhs3[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) rhs3[i] = v[i] + AT(b.faux, 4 * c + i) / dt;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          double t = 0.;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) t += AT(b.fP, r0 * 4 + 3 * i + j) * rhs3[j];
+          df[i] = -t;
+          AT(b.cforce, r0 + i) = f[i] + df[i];
+        }
+      } else {
+        double A4[16], P4[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { A4[i] = AT(b.fAcc, r0 * 4 + i); P4[i] = AT(b.fP, r0 * 4 + i); }
+        const int br = softfinger_solve(v, A4, P4, AT(b.faux, 4 * c), cd[36], cd + 37, dt, f, df, &status);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) AT(b.cforce, r0 + i) = f[i];
+        AT(b.fbranch, c) = br;
+      }
+      // y += T^T df ; u += Lambda[:, g..g+5] (T^T df)
+      for (int s = 0; s < 2; ++s) {
+        const int gs = s ? g0 : g1;
+        if (gs < 0) continue;
+        const double* Ts = s ? b.fT0 : b.fT1;
+        const double sign = s ? -1. : 1.;
+        double wv[6];
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+          double acc = 0.;
+          for (int i = 0; i < nd; ++i) acc += AT(Ts, c * 24 + i * 6 + p) * df[i];
+          wv[p] = sign * acc;
+          AT(b.fy, gs + p) += wv[p];
+        }
+        for (int g = 0; g < NG; ++g) {
+          double acc = 0.;
+#pragma unroll
+          for (int p = 0; p < 6; ++p) acc += AT(b.fLam, g * NG + gs + p) * wv[p];
+          AT(b.fu, g) += acc;
+        }
+      }
+    }
+  }
+  if (status) b.status[w] |= status;
+}
+
+// ---------------------------------------------------------------------------------------
+ARB_D void world_fused_finish(const DevModel& m, const DevBatch& b, int64_t w, double dt) {
+  const int64_t W = b.W;
+  const int n = m.ndof, NG = m.ngrows;
+  bool any = false;
+  for (int c = 0; c < m.nc; ++c) any = any || AT(b.factive, c);
+  bool finite = true;
+  for (int i = 0; i < n; ++i) {
+    double t = AT(b.fq, i);
+    if (any)
+      for (int g = 0; g < NG; ++g) {
+        const double yg = AT(b.fy, g);
+        if (yg != 0.) t += AT(b.fW, (int64_t)g * n + i) * yg;
+      }
+    AT(b.gvel, i) = t;
+    finite = finite && isfinite(t);
+  }
+  for (int j = 0; j < m.nj; ++j) {
+    const int type = m.jtype[j];
+    const int g = m.jgpos[j], d = m.jdof[j];
+    if (type == ARB_JOINT_FREE) {
+      double q[16], tw[6];
+      for (int i = 0; i < 16; ++i) q[i] = AT(b.gpos, g + i);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) tw[i] = dt * AT(b.gvel, d + i);
+      Se3 H, E, R;
+      se3_from16(q, H);
+      se3_exp(tw, E);
+      se3_mul(H, E, R);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) AT(b.gpos, g + 4 * r + c) = R.R[3 * r + c];
+        AT(b.gpos, g + 4 * r + 3) = R.p[r];
+      }
+    } else {
+      const int nd = arb_joint_ndof(type);
+      for (int i = 0; i < nd; ++i) AT(b.gpos, g + i) += dt * AT(b.gvel, d + i);
+    }
+  }
+  if (!finite) b.status[w] |= ARB_STATUS_NONFINITE;
+}

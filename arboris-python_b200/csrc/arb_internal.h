@@ -27,11 +27,13 @@ struct arb_batch {
   int* scratch_int = nullptr;
   int64_t launches = 0;
   int force_phases = 0;            // tests: run arb_step through the four phase kernels
+  int prepare_warp = 1;            // 0: lane-per-world prepare stage (tests, unsupported models)
   FusedState* fused = nullptr;
 };
 
 const char* arb_set_error(const std::string& s);
 int arb_step_phases(arb_batch* b, const double* dts, int nsteps);
+int arb_ensure_phase_scratch(arb_batch* b);
 // warp-per-world fused step (arb_fused.cu)
 bool arb_fused_supported(const arb_batch* b);
 int arb_fused_step(arb_batch* b, const double* dts, int nsteps);

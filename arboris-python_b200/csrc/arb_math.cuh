@@ -13,7 +13,7 @@
 // (tests/hosttest builds them with g++; the package never loads that build).
 #ifdef __CUDACC__
 #define ARB_HD __host__ __device__ __forceinline__
-#define ARB_NOINLINE __host__ __device__ __noinline__
+#define ARB_NOINLINE static __host__ __device__ __noinline__
 #else
 #define ARB_HD inline
 #define ARB_NOINLINE inline

@@ -13,6 +13,8 @@ struct HostModel {
   int ndof = 0, ngpos = 0, nj = 0, nc = 0, na = 0, nrows = 0, ncols = 0, maxk = 0, anyvisc = 0;
   std::vector<int> jtype, jparent, jdof, jgpos, hcn_ident, bflags, coloff, kcols, pathdof;
   std::vector<int> ctype, cint, crow, atype, aint;
+  std::vector<int> dofbody, dofpos, gen_body, cgen1, cgen0;
+  int ngen = 0, ngrows = 0;
   std::vector<double> Hpr, HprInv, Hcn, HcnInv, bmass, bvisc, brx, cdbl, adbl, ablob;
   double up[3] = {0., 1., 0.};
 };
@@ -115,6 +117,31 @@ static inline int build_host_model(const arb_model_desc* d, HostModel& m, std::s
   for (int a = 0; a < m.na; ++a)
     if (m.atype[a] != ARB_CTRL_WEIGHT && m.atype[a] != ARB_CTRL_PD) { err = "unknown controller type"; return -4; }
   for (int i = 0; i < 3; ++i) m.up[i] = d->up[i];
+  // fused-path tables
+  m.dofbody.assign(m.ndof, 0);
+  m.dofpos.assign(m.ndof, 0);
+  for (int j = 0; j < nj; ++j)
+    for (int i = 0; i < arb_joint_ndof(m.jtype[j]); ++i) {
+      m.dofbody[m.jdof[j] + i] = j + 1;
+      m.dofpos[m.jdof[j] + i] = m.kcols[m.jparent[j]] + i;
+    }
+  m.cgen1.assign(m.nc, -1);
+  m.cgen0.assign(m.nc, -1);
+  std::vector<int> body_gen(nj + 1, -1);
+  for (int c = 0; c < m.nc; ++c) {   // 6-row generators first, in order of first use
+    if (m.ctype[c] == ARB_CONS_JOINT_LIMITS) continue;
+    const int* ci = &m.cint[ARB_CONS_NINT * c];
+    for (int side = 1; side >= 0; --side) {
+      const int b = ci[side];
+      if (b == 0) continue;
+      if (body_gen[b] < 0) { body_gen[b] = 6 * (int)m.gen_body.size(); m.gen_body.push_back(b); }
+      (side ? m.cgen1 : m.cgen0)[c] = body_gen[b];
+    }
+  }
+  m.ngen = (int)m.gen_body.size();
+  m.ngrows = 6 * m.ngen;
+  for (int c = 0; c < m.nc; ++c)
+    if (m.ctype[c] == ARB_CONS_JOINT_LIMITS) m.cgen1[c] = m.ngrows++;
   return 0;
 }
 
@@ -137,6 +164,30 @@ static inline ScratchSizes scratch_sizes(const HostModel& m) {
   s.tmp = 2 * n;
   s.cactive = s.cbranch = s.cdol = nc; s.czidx = nc * 3;
   return s;
+}
+struct FusedSizes {
+  int64_t fq, fW, fLam, fv0, fT1, fT0, fu, fy, fAcc, fP, faux, fpose, factive, fbranch;
+  int64_t total_doubles() const { return fq + fW + fLam + fv0 + fT1 + fT0 + fu + fy + fAcc + fP + faux + fpose; }
+  int64_t total_ints() const { return factive + fbranch; }
+};
+static inline FusedSizes fused_sizes(const HostModel& m) {
+  FusedSizes s;
+  const int64_t n = m.ndof, NG = m.ngrows > 0 ? m.ngrows : 1, nc = m.nc > 0 ? m.nc : 1,
+                nr = m.nrows > 0 ? m.nrows : 1;
+  s.fq = n; s.fW = NG * n; s.fLam = NG * NG; s.fv0 = NG; s.fT1 = nc * 24; s.fT0 = nc * 24;
+  s.fu = NG; s.fy = NG; s.fAcc = nr * 4; s.fP = nr * 4; s.faux = nc * 4; s.fpose = (int64_t)m.nj * 12;
+  s.factive = nc; s.fbranch = nc;
+  return s;
+}
+static inline void carve_fused(const FusedSizes& s, int64_t W, double* dbl, int* ints, DevBatch& b) {
+  double* p = dbl;
+  auto take = [&](int64_t k) { double* r = p; p += k * W; return r; };
+  b.fq = take(s.fq); b.fW = take(s.fW); b.fLam = take(s.fLam); b.fv0 = take(s.fv0);
+  b.fT1 = take(s.fT1); b.fT0 = take(s.fT0); b.fu = take(s.fu); b.fy = take(s.fy);
+  b.fAcc = take(s.fAcc); b.fP = take(s.fP); b.faux = take(s.faux); b.fpose = take(s.fpose);
+  int* q = ints;
+  auto takei = [&](int64_t k) { int* r = q; q += k * W; return r; };
+  b.factive = takei(s.factive); b.fbranch = takei(s.fbranch);
 }
 // carve `dbl` (doubles) and `ints` into the DevBatch members; W worlds
 static inline void carve_scratch(const ScratchSizes& s, int64_t W, double* dbl, int* ints, DevBatch& b) {

@@ -42,6 +42,16 @@ struct DevModel {
   const int *atype, *aint;                     // controllers
   const double *adbl, *ablob;
   double up[3];
+  // ---- fused path tables -------------------------------------------------------------
+  // Z = M/dt + B + N has the tree's sparsity: Z[i][j] != 0 only if dofs i and j lie on a
+  // common root path.  dof k sits at position dofpos[k] of the path of body dofbody[k];
+  // its ancestors are pathdof[coloff[dofbody[k]] + 0 .. dofpos[k]-1].
+  const int *dofbody, *dofpos;                 // [ndof]
+  // "generators" of the constraint space: 6 rows (a body twist) per distinct moving body
+  // that carries a constraint frame, 1 row per limited joint dof.
+  int ngen, ngrows;                            // generator bodies, total rows NG
+  const int *gen_body;                         // [ngen]
+  const int *cgen1, *cgen0;                    // [nc] first generator row of body1 / body0 (or -1)
 };
 
 // Per-batch memory: caller-owned state + library-owned scratch, all [elem][W].
@@ -66,4 +76,16 @@ struct DevBatch {
   double *tmp;       // [2n]
   int *cactive, *cbranch, *cdol, *czidx /*[nc][3]*/;
   int *status;       // [W]
+  // ---- fused path (arb_fused.cuh): what the prepare stage hands to the Gauss-Seidel
+  // and finish stages, [elem][W] ------------------------------------------------------
+  double *fq;        // [n]        velocity without constraint forces  Z^-1 (M gvel/dt + gforce)
+  double *fW;        // [NG][n]    Z^-1 G^T, one n-vector per generator row
+  double *fLam;      // [NG][NG]   G Z^-1 G^T
+  double *fv0;       // [NG]       G fq
+  double *fT1, *fT0; // [nc][24]   d_c x 6 maps from the body twists to the constraint rows
+  double *fu, *fy;   // [NG]       generator-space velocity / accumulated wrench
+  double *fAcc, *fP; // [nrows][4] diagonal Delassus blocks and their pseudo-inverses
+  double *faux;      // [nc][4]
+  double *fpose;     // [nj][12]   body poses (for contacts and gravity)
+  int *factive, *fbranch;  // [nc]
 };

@@ -128,6 +128,9 @@ int arb_batch_create(const arb_model *model, int64_t nworlds, int device, void *
                      arb_batch **out);
 void arb_batch_destroy(arb_batch *batch);
 int arb_batch_set_stream(arb_batch *batch, void *stream);
+/* tuning/testing switches: "force_phases" (1: arb_step runs the four API phase kernels
+ * instead of the fused stages), "prepare_warp" (0: lane-per-world prepare stage) */
+int arb_batch_set_option(arb_batch *batch, const char *name, int value);
 
 /* caller-owned DEVICE state, layouts in the header comment */
 int arb_batch_bind_state(arb_batch *batch, double *gpos, double *gvel, double *cforce);

@@ -9,6 +9,7 @@
 #include <vector>
 #include "../../arboris-python_b200/csrc/arb_model_host.h"
 #include "../../arboris-python_b200/csrc/arb_world.cuh"
+#include "../../arboris-python_b200/csrc/arb_fused.cuh"
 
 static DevModel view(const HostModel& h) {
   DevModel m;
@@ -21,6 +22,8 @@ static DevModel view(const HostModel& h) {
   m.ctype = h.ctype.data(); m.cint = h.cint.data(); m.crow = h.crow.data(); m.cdbl = h.cdbl.data();
   m.atype = h.atype.data(); m.aint = h.aint.data(); m.adbl = h.adbl.data(); m.ablob = h.ablob.data();
   for (int i = 0; i < 3; ++i) m.up[i] = h.up[i];
+  m.dofbody = h.dofbody.data(); m.dofpos = h.dofpos.data(); m.ngen = h.ngen; m.ngrows = h.ngrows;
+  m.gen_body = h.gen_body.data(); m.cgen1 = h.cgen1.data(); m.cgen0 = h.cgen0.data();
   return m;
 }
 
@@ -28,8 +31,8 @@ struct HostBatch {
   HostModel hm;
   DevModel dm;
   DevBatch b;
-  std::vector<double> dbl;
-  std::vector<int> ints, status;
+  std::vector<double> dbl, fdbl;
+  std::vector<int> ints, fints, status;
 };
 
 extern "C" {
@@ -50,6 +53,10 @@ void* ht_create(const arb_model_desc* d, int64_t W, char* errbuf, int errlen) {
   hb->b.W = W;
   carve_scratch(s, W, hb->dbl.data(), hb->ints.data(), hb->b);
   hb->b.status = hb->status.data();
+  FusedSizes fs = fused_sizes(hb->hm);
+  hb->fdbl.assign(fs.total_doubles() * W, 0.);
+  hb->fints.assign(fs.total_ints() * W, 0);
+  carve_fused(fs, W, hb->fdbl.data(), hb->fints.data(), hb->b);
   return hb;
 }
 void ht_destroy(void* p) { delete (HostBatch*)p; }
@@ -73,6 +80,16 @@ void ht_integrate(void* p, double dt) {
   HostBatch* hb = (HostBatch*)p;
   for (int64_t w = 0; w < hb->b.W; ++w) world_integrate(hb->dm, hb->b, w, dt);
 }
+// the fused step in its scalar form: update_dynamic, prepare, gs, finish
+void ht_fused_step(void* p, double dt) {
+  HostBatch* hb = (HostBatch*)p;
+  for (int64_t w = 0; w < hb->b.W; ++w) {
+    world_update_dynamic(hb->dm, hb->b, w);
+    world_fused_prepare(hb->dm, hb->b, w, dt);
+    world_fused_gs(hb->dm, hb->b, w, dt);
+    world_fused_finish(hb->dm, hb->b, w, dt);
+  }
+}
 // raw scratch access: which = index into the DevBatch double members in declaration order
 double* ht_array(void* p, const char* name) {
   HostBatch* hb = (HostBatch*)p;
@@ -91,6 +108,7 @@ int* ht_iarray(void* p, const char* name) {
   std::string s(name);
   if (s == "cactive") return b.cactive; if (s == "cbranch") return b.cbranch; if (s == "cdol") return b.cdol;
   if (s == "czidx") return b.czidx; if (s == "status") return b.status;
+  if (s == "factive") return b.factive; if (s == "fbranch") return b.fbranch;
   return nullptr;
 }
 void ht_pinv(int n, const double* a, double* out) {

@@ -39,7 +39,7 @@ def lib():
         L.ht_bind.argtypes = [C.c_void_p] * 4
         for f in ("ht_update_dynamic",):
             getattr(L, f).argtypes = [C.c_void_p]
-        for f in ("ht_update_controllers", "ht_update_constraints", "ht_integrate"):
+        for f in ("ht_update_controllers", "ht_update_constraints", "ht_integrate", "ht_fused_step"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_double]
         L.ht_array.restype = C.POINTER(C.c_double)
         L.ht_array.argtypes = [C.c_void_p, C.c_char_p]
@@ -79,6 +79,9 @@ class HostBatch(object):
 
     def integrate(self, dt):
         self.L.ht_integrate(self.h, dt)
+
+    def fused_step(self, dt):
+        self.L.ht_fused_step(self.h, dt)
 
     def arr(self, name, *shape):
         p = self.L.ht_array(self.h, name.encode())

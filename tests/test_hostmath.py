@@ -126,3 +126,37 @@ def test_solve4_and_exp():
         H = twist_exp(tw)
         assert np.abs(out[:9].reshape(3, 3) - H[:3, :3]).max() < 1e-14
         assert np.abs(out[9:] - H[:3, 3]).max() < 1e-13*max(1., np.abs(H[:3, 3]).max())
+
+
+@pytest.mark.parametrize("name,tol", [("simplearm", 1e-12), ("human36_free", 1e-10),
+                                      ("ball_socket", 1e-12), ("simplearm_limits", 1e-12),
+                                      ("snake_loop", 1e-10), ("human36_contact", 1e-10)])
+def test_fused_algorithm_vs_real_reference(name, tol):
+    """The fused step's algorithm in scalar form (no-fill tree factorisation of Z instead of
+    the explicit inverse, Gauss-Seidel in generator space) against the real reference."""
+    model, tr = load_golden(name)
+    dt = float(tr["dt"])
+    W, T = tr["gpos"].shape[:2]
+    hb = harness.HostBatch(model, W)
+    gpos, gvel = tr["gpos_in"].T.copy(), tr["gvel_in"].T.copy()
+    cf = np.zeros((max(model.nrows, 1), W))
+    flips, worst = 0, {}
+    for s in range(T):
+        hb.gpos[:], hb.gvel[:], hb.cforce[:] = gpos, gvel, cf
+        hb.fused_step(dt)
+        if model.nc:
+            a = hb.iarr("factive", model.nc).T
+            br = hb.iarr("fbranch", model.nc).T
+            flips += int((a != tr["active"][:, s]).sum()) + int((br*a != tr["branch"][:, s]).sum())
+            if name != "ball_socket":
+                worst["cforce"] = max(worst.get("cforce", 0),
+                                      rel(hb.cforce.T[:, :model.nrows], tr["cforce"][:, s]))
+        worst["gvel"] = max(worst.get("gvel", 0), rel(hb.gvel.T, tr["gvel"][:, s]))
+        worst["gpos"] = max(worst.get("gpos", 0), rel(hb.gpos.T, tr["gpos"][:, s]))
+        gpos, gvel = tr["gpos"][:, s].T.copy(), tr["gvel"][:, s].T.copy()
+        if model.nrows:
+            cf = tr["cforce"][:, s].T.copy()
+    assert flips == 0
+    assert not hb.iarr("status").any()
+    for k, v in worst.items():
+        assert v <= tol, (k, v)
