@@ -66,6 +66,13 @@ static int model_to_device(arb_model* mo, int device) {
   rc |= upload(h.gen_body, &m.gen_body, own);
   rc |= upload(h.cgen1, &m.cgen1, own);   rc |= upload(h.cgen0, &m.cgen0, own);
   m.ngen = h.ngen; m.ngrows = h.ngrows;
+  rc |= upload(h.dofjoint, &m.dofjoint, own);   rc |= upload(h.jhaschild, &m.jhaschild, own);
+  rc |= upload(h.jaccfirst, &m.jaccfirst, own); rc |= upload(h.jmark, &m.jmark, own);
+  rc |= upload(h.jmarkfirst, &m.jmarkfirst, own); rc |= upload(h.jmarkchild, &m.jmarkchild, own);
+  rc |= upload(h.glimdof, &m.glimdof, own);     rc |= upload(h.pd_gpos, &m.pd_gpos, own);
+  rc |= upload(h.pd_kp, &m.pd_kp, own);         rc |= upload(h.pd_kd, &m.pd_kd, own);
+  rc |= upload(h.pd_qd, &m.pd_qd, own);         rc |= upload(h.pd_c, &m.pd_c, own);
+  m.has_pd = h.has_pd; m.gravity = h.gravity; m.nweight = h.nweight;
   if (rc) return -100;
   for (int i = 0; i < 3; ++i) m.up[i] = h.up[i];
   mo->dev[device] = m;

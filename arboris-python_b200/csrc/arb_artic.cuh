@@ -1,0 +1,556 @@
+// Articulated-body form of the step: the same linear system the reference solves with
+// the assembled matrices,
+//     Z q'+ = M q'/dt + g + J^T f ,   Z = M/dt + B + N                   (core.py:813-818, 975-976)
+// solved WITHOUT assembling M, N, B or Z, in O(ndof) per right-hand side.
+//
+// Derivation (each identity is checked against the real reference by the parity tests).
+// Body Jacobians obey  J_c = X_c J_p (+ own columns S_c),  X_c = Ad(H_pc^-1), and the
+// reference's  dJ_c = dAd_cp J_p + X_c dJ_p (+ own columns dS_c)  (core.py:1309-1313) with
+//     dAd_cp = Ad_cn Ad_nr adjacency(-Ad_nr T_nr) Ad_rp = adjacency(tau_c) X_c ,
+//     tau_c  = -Ad_cn Ad_nr Ad_nr T_nr                                  (rigidmotion.py:49-75).
+// Summing along a root path gives, with theta_c = X_c theta_p + tau_c,
+//     dJ_b[:,k] = adjacency(theta_b) J_b[:,k] + X_(b<-c_k) s^_k ,  s^_k = ds_k - adjacency(theta_(c_k)) s_k
+// so that with  Jh_b[:,k] = X_(b<-c_k) s^_k  (a second "Jacobian" with the same recursion)
+//     Z = sum_b J_b^T ( A_b J_b + M_b Jh_b ) ,   A_b = M_b/dt + B_b + N_b + M_b adjacency(theta_b)
+// (N_b from core.py:1276-1288).  For a vector x the body quantities V_b = J_b x, Vh_b = Jh_b x
+// follow  V_c = X_c V_p + S_c x_c,  Vh_c = X_c Vh_p + S^_c x_c,  and  (Z x)_k = s_k^T F_(c_k) with
+// F_b = A_b V_b + M_b Vh_b + sum_children X^T F.  Eliminating the dofs leaf-to-root, one
+// scalar dof at a time (exact Gaussian elimination, no fill-in), keeps F of the form
+//     F_b = IA_b V_b + IM_b Vh_b + beta_b :
+//     U_k = IA s_k + IM s^_k ,  d_k = s_k^T U_k ,  x_k = (tau_k - s_k^T(IA V + IM Vh + beta)) / d_k
+//     IA <- IA - U_k (s_k^T IA)/d_k ,  IM <- IM - U_k (s_k^T IM)/d_k ,  beta <- beta + U_k u_k
+//     parent:  IA_p += X^T IA X ,  IM_p += X^T IM X ,  beta_p += X^T beta .
+// Right-hand sides are generalized forces tau_k plus body wrenches w_b (beta_b starts at -w_b):
+// the free motion uses w_b = M_b (T_b/dt + gravity_b)  (M q' = sum J_b^T M_b T_b,
+// controllers.py:43-60), the constraint generators use unit wrenches on the bodies that
+// carry constraint frames, and the final velocity uses the Gauss-Seidel wrenches.
+//
+// One world per lane; every array is [elem][W] (coalesced over the lanes of a warp).
+#pragma once
+#include "arb_constraints.cuh"
+#include "arb_joints.cuh"
+#include "arb_math.cuh"
+#include "arb_types.h"
+
+#ifndef AT
+#define AT(ptr, idx) (ptr)[(int64_t)(idx) * W + w]
+#endif
+
+// y = X^T x for a wrench x = [m; f], X = Ad(H^-1):  [R m + p x (R f) ; R f]
+ARB_HD void wrench_up(const Se3& h, const double* x, double* y) {
+  double rm[3], rf[3], c[3];
+  m3_mulv(h.R, x, rm);
+  m3_mulv(h.R, x + 3, rf);
+  cross3(h.p, rf, c);
+  y[0] = rm[0] + c[0]; y[1] = rm[1] + c[1]; y[2] = rm[2] + c[2];
+  y[3] = rf[0]; y[4] = rf[1]; y[5] = rf[2];
+}
+// A <- X^T A X  (6x6 row-major), X = Ad(H^-1)
+ARB_HD void congruence_up(const Se3& h, double* A) {
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {  // rows:  row_r(A X) = (X^T row_r(A)^T)^T
+    double y[6];
+    wrench_up(h, A + 6 * r, y);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) A[6 * r + i] = y[i];
+  }
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {  // columns
+    double x[6], y[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) x[i] = A[6 * i + c];
+    wrench_up(h, x, y);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) A[6 * i + c] = y[i];
+  }
+}
+// y = adjacency(t) x = [w x xw ; v x xw + w x xv]      (twistvector.py:26-33)
+ARB_HD void adj_apply(const double* t, const double* x, double* y) {
+  double a[3], b2[3], c[3];
+  cross3(t, x, a);
+  cross3(t + 3, x, b2);
+  cross3(t, x + 3, c);
+  y[0] = a[0]; y[1] = a[1]; y[2] = a[2];
+  y[3] = b2[0] + c[0]; y[4] = b2[1] + c[1]; y[5] = b2[2] + c[2];
+}
+
+ARB_D void load_se3(const double* arr, int j, int64_t W, int64_t w, Se3& h) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) h.R[i] = AT(arr, j * 12 + i);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) h.p[i] = AT(arr, j * 12 + 9 + i);
+}
+ARB_D void store_se3(double* arr, int j, int64_t W, int64_t w, const Se3& h) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) AT(arr, j * 12 + i) = h.R[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) AT(arr, j * 12 + 9 + i) = h.p[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// root-to-leaf pass: body poses and twists (core.py:1295-1308), theta, X, s, s^
+ARB_D void artic_kinematics(const DevModel& m, const DevBatch& b, int64_t w) {
+  const int64_t W = b.W;
+  for (int j = 0; j < m.nj; ++j) {
+    const int type = m.jtype[j];
+    const int par = m.jparent[j];
+    const int nd = arb_joint_ndof(type);
+    const int dof = m.jdof[j];
+    double q[16], dq[6];
+    for (int i = 0; i < arb_joint_ngpos(type); ++i) q[i] = AT(b.gpos, m.jgpos[j] + i);
+    for (int i = 0; i < nd; ++i) dq[i] = AT(b.gvel, dof + i);
+    JointKin k;
+    joint_kinematics(type, q, dq, k);
+    const bool ident = m.hcn_ident[j] != 0;
+    Se3 Hpr, Hcn, Hpc, Hgc, t0;
+    load_se3_const(m.Hpr, j, Hpr);
+    se3_mul(Hpr, k.H, t0);
+    if (ident) {
+      Hpc = t0;
+      se3_identity(Hcn);
+    } else {
+      Se3 HcnInv;
+      load_se3_const(m.HcnInv, j, HcnInv);
+      load_se3_const(m.Hcn, j, Hcn);
+      se3_mul(t0, HcnInv, Hpc);
+    }
+    double Tp[6], thp[6];
+    if (par == 0) {
+      Hgc = Hpc;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { Tp[i] = 0.; thp[i] = 0.; }
+    } else {
+      Se3 Hgp;
+      load_se3(b.fpose, par - 1, W, w, Hgp);
+      se3_mul(Hgp, Hpc, Hgc);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { Tp[i] = AT(b.atw, (par - 1) * 6 + i); thp[i] = AT(b.ath, (par - 1) * 6 + i); }
+    }
+    store_se3(b.fpose, j, W, w, Hgc);
+    store_se3(b.aX, j, W, w, Hpc);
+    // child twist = Ad_cp T_p + Ad_cn T_nr                               (core.py:1308)
+    double ta[6], tb[6], th[6];
+    iad_apply(Hpc, Tp, ta);
+    if (ident) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) tb[i] = k.T[i];
+    } else {
+      ad_apply(Hcn, k.T, tb);
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) AT(b.atw, j * 6 + i) = ta[i] + tb[i];
+    // theta_c = X_c theta_p - Ad_cn Ad_nr Ad_nr T_nr
+    {
+      Se3 Hnr;
+      se3_inv(k.H, Hnr);
+      double t1[6], t2[6], tau[6];
+      ad_apply(Hnr, k.T, t1);
+      ad_apply(Hnr, t1, t2);
+      if (ident) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) tau[i] = t2[i];
+      } else {
+        ad_apply(Hcn, t2, tau);
+      }
+      iad_apply(Hpc, thp, ta);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { th[i] = ta[i] - tau[i]; AT(b.ath, j * 6 + i) = th[i]; }
+    }
+    // own columns: s = Ad_cn S, s^ = Ad_cn dS - adjacency(theta) s         (core.py:1310,1313)
+    for (int c = 0; c < nd; ++c) {
+      double s0[6], ds0[6], s[6], ds[6], as[6];
+      if (type == ARB_JOINT_FREE) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { s0[i] = (i == c) ? 1. : 0.; ds0[i] = 0.; }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { s0[i] = k.S[6 * c + i]; ds0[i] = k.dS[6 * c + i]; }
+      }
+      if (ident) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { s[i] = s0[i]; ds[i] = ds0[i]; }
+      } else {
+        ad_apply(Hcn, s0, s);
+        ad_apply(Hcn, ds0, ds);
+      }
+      adj_apply(th, s, as);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        AT(b.aS, (dof + c) * 6 + i) = s[i];
+        AT(b.aSh, (dof + c) * 6 + i) = ds[i] - as[i];
+      }
+    }
+  }
+}
+
+// generalized force of the (diagonal) PD controllers on dof k        (controllers.py:141-159)
+ARB_D double artic_tau(const DevModel& m, const DevBatch& b, int64_t w, int k) {
+  const int64_t W = b.W;
+  if (!m.has_pd || m.pd_gpos[k] < 0) return 0.;
+  return m.pd_kp[k] * (m.pd_qd[k] - AT(b.gpos, m.pd_gpos[k])) + m.pd_c[k];
+}
+
+// ---------------------------------------------------------------------------------------
+// leaf-to-root pass: elimination of every dof (stores U, LA, LM, 1/d) together with the
+// reduced right-hand side u of the free motion (w_b = M_b (T_b/dt + gravity_b), tau = PD).
+ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double dt) {
+  const int64_t W = b.W;
+  bool ok = true;
+  const double gt[6] = {0., 0., 0., m.gravity * m.up[0], m.gravity * m.up[1], m.gravity * m.up[2]};
+  for (int j = m.nj - 1; j >= 0; --j) {
+    const int type = m.jtype[j];
+    const int par = m.jparent[j];
+    const int nd = arb_joint_ndof(type);
+    const int dof = m.jdof[j];
+    const int flags = m.bflags[j];
+    const double* Mb = m.bmass + 36 * j;
+    double IA[36], IM[36], beta[6];
+    double T[6], th[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { T[i] = AT(b.atw, j * 6 + i); th[i] = AT(b.ath, j * 6 + i); }
+    if (flags & ARB_BODY_HASMASS) {
+      // A_b = M_b/dt + B_b + Omega(T) M_b + M_b adjacency(theta)
+      double X3[9];
+      {
+        double wx[9], t1[9], t2[9];
+        skew3(T, wx);
+        m3_mul(m.brx + 9 * j, wx, t1);
+        m3_mul(wx, m.brx + 9 * j, t2);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) X3[i] = t1[i] - t2[i];
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {  // Omega M, column by column
+        double top[3] = {Mb[c], Mb[6 + c], Mb[12 + c]}, bot[3] = {Mb[18 + c], Mb[24 + c], Mb[30 + c]};
+        double a[3], x2[3], d[3];
+        cross3(T, top, a);
+        m3_mulv(X3, bot, x2);
+        cross3(T, bot, d);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { IA[6 * i + c] = a[i] + x2[i]; IA[6 * (i + 3) + c] = d[i]; }
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {  // M adjacency(theta), row by row: [a1 x w + a2 x v, a2 x w]
+        const double* a1 = Mb + 6 * r;
+        const double* a2 = Mb + 6 * r + 3;
+        double c1[3], c2[3], c3[3];
+        cross3(a1, th, c1);
+        cross3(a2, th + 3, c2);
+        cross3(a2, th, c3);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { IA[6 * r + i] += c1[i] + c2[i]; IA[6 * r + 3 + i] += c3[i]; }
+      }
+#pragma unroll
+      for (int i = 0; i < 36; ++i) { IA[i] += Mb[i] / dt; IM[i] = Mb[i]; }
+      // -w_b = -M_b (T/dt + gravity_b)
+      double a[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) a[i] = T[i] / dt;
+      if ((flags & ARB_BODY_MASSIVE) && m.nweight > 0) {
+        Se3 H;
+        load_se3(b.fpose, j, W, w, H);
+        double g[6];
+        iad_apply(H, gt, g);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) a[i] += g[i];
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        double t = 0.;
+#pragma unroll
+        for (int c = 0; c < 6; ++c) t += Mb[6 * r + c] * a[c];
+        beta[r] = -t;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 36; ++i) { IA[i] = 0.; IM[i] = 0.; }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) beta[i] = 0.;
+    }
+    if (flags & ARB_BODY_HASVISC) {
+      const double* Bb = m.bvisc + 36 * j;
+#pragma unroll
+      for (int i = 0; i < 36; ++i) IA[i] += Bb[i];
+    }
+    if (m.jhaschild[j]) {
+#pragma unroll
+      for (int i = 0; i < 36; ++i) { IA[i] += AT(b.aIA, j * 36 + i); IM[i] += AT(b.aIM, j * 36 + i); }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) beta[i] += AT(b.abeta, j * 6 + i);
+    }
+    for (int c = nd - 1; c >= 0; --c) {
+      const int k = dof + c;
+      double s[6], sh[6], U[6], LA[6], LM[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { s[i] = AT(b.aS, k * 6 + i); sh[i] = AT(b.aSh, k * 6 + i); }
+      double d = 0., sb = 0.;
+#pragma unroll
+      for (int r = 0; r < 6; ++r) {
+        double t = 0.;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) t += IA[6 * r + i] * s[i] + IM[6 * r + i] * sh[i];
+        U[r] = t;
+        d += s[r] * t;
+        sb += s[r] * beta[r];
+      }
+      if (m.has_pd) d += dt * m.pd_kp[k] + m.pd_kd[k];
+      if (!(fabs(d) > 0.)) ok = false;
+      const double dinv = 1. / d;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        double ta = 0., tm = 0.;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) { ta += s[r] * IA[6 * r + i]; tm += s[r] * IM[6 * r + i]; }
+        LA[i] = ta * dinv;
+        LM[i] = tm * dinv;
+      }
+      const double u = (artic_tau(m, b, w, k) - sb) * dinv;
+      AT(b.au, k) = u;
+      AT(b.adinv, k) = dinv;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { AT(b.aU, k * 6 + i) = U[i]; AT(b.aLA, k * 6 + i) = LA[i]; AT(b.aLM, k * 6 + i) = LM[i]; }
+      if (c > 0 || par != 0) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) { IA[6 * r + i] -= U[r] * LA[i]; IM[6 * r + i] -= U[r] * LM[i]; }
+          beta[r] += U[r] * u;
+        }
+      }
+    }
+    if (par != 0) {
+      Se3 X;
+      load_se3(b.aX, j, W, w, X);
+      congruence_up(X, IA);
+      congruence_up(X, IM);
+      double bu[6];
+      wrench_up(X, beta, bu);
+      const int pj = par - 1;
+      if (m.jaccfirst[j]) {
+#pragma unroll
+        for (int i = 0; i < 36; ++i) { AT(b.aIA, pj * 36 + i) = IA[i]; AT(b.aIM, pj * 36 + i) = IM[i]; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) AT(b.abeta, pj * 6 + i) = bu[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 36; ++i) { AT(b.aIA, pj * 36 + i) += IA[i]; AT(b.aIM, pj * 36 + i) += IM[i]; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) AT(b.abeta, pj * 6 + i) += bu[i];
+      }
+    }
+  }
+  return ok;
+}
+
+// ---------------------------------------------------------------------------------------
+// root-to-leaf pass for ONE right-hand side over ALL joints:  x_k = u_k - LA_k V - LM_k Vh.
+// u_k is read from `u` for marked joints (or all joints if !marked_u), else 0.  x is written
+// to `x`; (V, Vh) of every body with children is kept in aV[j][0..11].
+template <bool MARKED_U>
+ARB_D void artic_forward_full(const DevModel& m, const DevBatch& b, int64_t w, const double* u, double* x) {
+  const int64_t W = b.W;
+  for (int j = 0; j < m.nj; ++j) {
+    const int par = m.jparent[j];
+    const int nd = arb_joint_ndof(m.jtype[j]);
+    const int dof = m.jdof[j];
+    double V[6], Vh[6];
+    if (par == 0) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { V[i] = 0.; Vh[i] = 0.; }
+    } else {
+      Se3 X;
+      load_se3(b.aX, j, W, w, X);
+      double vp[6], vhp[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { vp[i] = AT(b.aV, (par - 1) * 72 + i); vhp[i] = AT(b.aV, (par - 1) * 72 + 6 + i); }
+      iad_apply(X, vp, V);
+      iad_apply(X, vhp, Vh);
+    }
+    const bool useu = !MARKED_U || m.jmark[j];
+    for (int c = 0; c < nd; ++c) {
+      const int k = dof + c;
+      double t = useu ? AT(u, k) : 0.;
+      if (par != 0 || c > 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) t -= AT(b.aLA, k * 6 + i) * V[i] + AT(b.aLM, k * 6 + i) * Vh[i];
+      }
+      AT(x, k) = t;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { V[i] += AT(b.aS, k * 6 + i) * t; Vh[i] += AT(b.aSh, k * 6 + i) * t; }
+    }
+    if (m.jhaschild[j] || m.jmark[j]) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { AT(b.aV, j * 72 + i) = V[i]; AT(b.aV, j * 72 + 6 + i) = Vh[i]; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// NR right-hand sides that start on ONE root path (unit wrenches on body `body`, or a unit
+// generalized force on dof `kstart`), restricted to the marked joints:
+//  backward along the path (u stored in au[r][k] for the path dofs), then forward over the
+//  marked joints.  (V of each marked body is left in aV[j][r*12 ..], x in ax[r][k].)
+template <int NR>
+ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t w, int body, int kstart) {
+  const int64_t W = b.W;
+  const int n = m.ndof;
+  const int off = m.coloff[body];
+  double beta[NR][6];
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) beta[r][i] = (kstart < 0 && i == r) ? -1. : 0.;
+  const int l0 = (kstart < 0) ? m.kcols[body] - 1 : m.dofpos[kstart];
+  for (int l = l0; l >= 0; --l) {
+    const int k = m.pathdof[off + l];
+    const int j = m.dofjoint[k];
+    double s[6], U[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { s[i] = AT(b.aS, k * 6 + i); U[i] = AT(b.aU, k * 6 + i); }
+    const double dinv = AT(b.adinv, k);
+    const bool last = (l == 0);
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      double sb = 0.;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) sb += s[i] * beta[r][i];
+      const double tau = (k == kstart) ? 1. : 0.;
+      const double u = (tau - sb) * dinv;
+      AT(b.au, r * n + k) = u;
+      if (!last) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) beta[r][i] += U[i] * u;
+      }
+    }
+    if (k == m.jdof[j] && m.jparent[j] != 0) {
+      Se3 X;
+      load_se3(b.aX, j, W, w, X);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        double y[6];
+        wrench_up(X, beta[r], y);
+#pragma unroll
+        for (int i = 0; i < 6; ++i) beta[r][i] = y[i];
+      }
+    }
+  }
+  // forward over the marked joints
+  const int kc = l0 + 1;   // path dofs 0..l0 carry a non-zero u
+  for (int j = 0; j < m.nj; ++j) {
+    if (!m.jmark[j]) continue;
+    const int par = m.jparent[j];
+    const int nd = arb_joint_ndof(m.jtype[j]);
+    const int dof = m.jdof[j];
+    double V[NR][6], Vh[NR][6];
+    if (par == 0) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { V[r][i] = 0.; Vh[r][i] = 0.; }
+    } else {
+      Se3 X;
+      load_se3(b.aX, j, W, w, X);
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        double vp[6], vhp[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          vp[i] = AT(b.aV, (par - 1) * 72 + r * 12 + i);
+          vhp[i] = AT(b.aV, (par - 1) * 72 + r * 12 + 6 + i);
+        }
+        iad_apply(X, vp, V[r]);
+        iad_apply(X, vhp, Vh[r]);
+      }
+    }
+    for (int c = 0; c < nd; ++c) {
+      const int k = dof + c;
+      const int pos = m.dofpos[k];
+      const bool onpath = pos < kc && m.pathdof[off + pos] == k;
+      double LA[6], LM[6], s[6], sh[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        LA[i] = AT(b.aLA, k * 6 + i); LM[i] = AT(b.aLM, k * 6 + i);
+        s[i] = AT(b.aS, k * 6 + i); sh[i] = AT(b.aSh, k * 6 + i);
+      }
+#pragma unroll
+      for (int r = 0; r < NR; ++r) {
+        double t = onpath ? AT(b.au, r * n + k) : 0.;
+        if (par != 0 || c > 0) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) t -= LA[i] * V[r][i] + LM[i] * Vh[r][i];
+        }
+        AT(b.ax, r * n + k) = t;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { V[r][i] += s[i] * t; Vh[r][i] += sh[i] * t; }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        AT(b.aV, j * 72 + r * 12 + i) = V[r][i];
+        AT(b.aV, j * 72 + r * 12 + 6 + i) = Vh[r][i];
+      }
+  }
+}
+
+// row `g` of the generator matrix G applied to the solution r of the last solve:
+// body generators read V of their body, joint-limit generators the dof itself.
+ARB_D double artic_gen_value(const DevModel& m, const DevBatch& b, int64_t w, int g, int r, const double* x) {
+  const int64_t W = b.W;
+  if (g < 6 * m.ngen) return AT(b.aV, (m.gen_body[g / 6] - 1) * 72 + r * 12 + g % 6);
+  return AT(x, r * m.ndof + m.glimdof[g - 6 * m.ngen]);
+}
+
+// ---------------------------------------------------------------------------------------
+// leaf-to-root pass over the marked joints for the Gauss-Seidel result y (wrenches on the
+// generator bodies, generalized forces on the limited dofs): u -> au[0][k] (marked dofs).
+ARB_D void artic_backward_wrenches(const DevModel& m, const DevBatch& b, int64_t w, const double* y) {
+  const int64_t W = b.W;
+  const int NG6 = 6 * m.ngen;
+  for (int j = m.nj - 1; j >= 0; --j) {
+    if (!m.jmark[j]) continue;
+    const int par = m.jparent[j];
+    const int nd = arb_joint_ndof(m.jtype[j]);
+    const int dof = m.jdof[j];
+    double beta[6] = {0., 0., 0., 0., 0., 0.};
+    for (int g = 0; g < m.ngen; ++g)
+      if (m.gen_body[g] == j + 1) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) beta[i] -= AT(y, 6 * g + i);
+      }
+    if (m.jmarkchild[j]) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) beta[i] += AT(b.abeta, j * 6 + i);
+    }
+    for (int c = nd - 1; c >= 0; --c) {
+      const int k = dof + c;
+      double tau = 0.;
+      for (int g = NG6; g < m.ngrows; ++g)
+        if (m.glimdof[g - NG6] == k) tau += AT(y, g);
+      double sb = 0.;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) sb += AT(b.aS, k * 6 + i) * beta[i];
+      const double u = (tau - sb) * AT(b.adinv, k);
+      AT(b.au, k) = u;
+      if (c > 0 || par != 0) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) beta[i] += AT(b.aU, k * 6 + i) * u;
+      }
+    }
+    if (par != 0) {
+      Se3 X;
+      load_se3(b.aX, j, W, w, X);
+      double bu[6];
+      wrench_up(X, beta, bu);
+      const int pj = par - 1;
+      if (m.jmarkfirst[j]) {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) AT(b.abeta, pj * 6 + i) = bu[i];
+      } else {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) AT(b.abeta, pj * 6 + i) += bu[i];
+      }
+    }
+  }
+}

@@ -131,33 +131,38 @@ ARB_D int softfinger_solve(const double* v, const double* A, const double* P, do
     beta[i] = alpha[i] - alpha[3] / yn * Yc[i];
     bb[i] = mu / yn * Yc[i];
   }
-  const double ycyc = Yc[0] * Yc[0] + Yc[1] * Yc[1] + Yc[2] * Yc[2];
-  const double betab = beta[0] * bb[0] + beta[1] * bb[1] + beta[2] * bb[2];
-  const double betabeta = beta[0] * beta[0] + beta[1] * beta[1] + beta[2] * beta[2];
-  const double bdotb = bb[0] * bb[0] + bb[1] * bb[1] + bb[2] * bb[2];
-  double Bm[36];
-#pragma unroll
-  for (int i = 0; i < 3; ++i)
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const double e2 = eps[i] * eps[i];
-      const double yhat = A[4 * i + j] - ycyc / yn;
-      Bm[6 * (3 + i) + 3 + j] = e2 * yhat;
-      Bm[6 * i + j] = e2 * (yhat + 2. / a * betab);
-      // dot(E, scalar) is E*scalar in numpy: these two blocks are DIAGONAL
-      Bm[6 * i + 3 + j] = (i == j) ? -(e2 * (betabeta / (a * a))) : 0.;
-      Bm[6 * (3 + i) + j] = (i == j) ? e2 * bdotb - 1. : 0.;
-    }
-  double wr[6], wi[6];
-  if (!eig_real_general6(Bm, wr, wi)) *status |= ARB_STATUS_EIG_NOCONV;
   double s = 0.;
   bool found = false;
+  const bool unit_eps = (eps[0] == 1. && eps[1] == 1. && eps[2] == 1.);
+  if (!(unit_eps && sliding_root_structured(A, alpha, mu, &s, &found))) {
+    const double ycyc = Yc[0] * Yc[0] + Yc[1] * Yc[1] + Yc[2] * Yc[2];
+    const double betab = beta[0] * bb[0] + beta[1] * bb[1] + beta[2] * bb[2];
+    const double betabeta = beta[0] * beta[0] + beta[1] * beta[1] + beta[2] * beta[2];
+    const double bdotb = bb[0] * bb[0] + bb[1] * bb[1] + bb[2] * bb[2];
+    double Bm[36];
 #pragma unroll
-  for (int i = 0; i < 6; ++i)
-    if (wi[i] == 0. && wr[i] <= 0.) {
-      if (!found || wr[i] < s) s = wr[i];
-      found = true;
-    }
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double e2 = eps[i] * eps[i];
+        const double yhat = A[4 * i + j] - ycyc / yn;
+        Bm[6 * (3 + i) + 3 + j] = e2 * yhat;
+        Bm[6 * i + j] = e2 * (yhat + 2. / a * betab);
+        // dot(E, scalar) is E*scalar in numpy: these two blocks are DIAGONAL
+        Bm[6 * i + 3 + j] = (i == j) ? -(e2 * (betabeta / (a * a))) : 0.;
+        Bm[6 * (3 + i) + j] = (i == j) ? e2 * bdotb - 1. : 0.;
+      }
+    double wr[6], wi[6];
+    if (!eig_real_general6(Bm, wr, wi)) *status |= ARB_STATUS_EIG_NOCONV;
+    found = false;
+    s = 0.;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (wi[i] == 0. && wr[i] <= 0.) {
+        if (!found || wr[i] < s) s = wr[i];
+        found = true;
+      }
+  }
   if (!found) { s = -1e10; *status |= ARB_STATUS_EIG_NOROOT; }
   if (s < -1e10) s = -1e10;
   double A2[16], nalpha[4], newf[4];

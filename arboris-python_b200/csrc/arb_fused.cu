@@ -1,6 +1,5 @@
 // Fused step driver: prepare -> gs -> finish per time step (see arb_fused.cuh).
-// prepare runs warp-per-world (arb_prepare_warp.cuh) when the model fits that kernel's
-// limits, else lane-per-world; gs and finish are lane-per-world.
+// All three stages are lane-per-world (one world per thread, [elem][W] arrays).
 #include <cuda_runtime.h>
 #include <string>
 
@@ -26,7 +25,6 @@ struct FusedState {
 __global__ void __launch_bounds__(FUSED_THREADS) k_fused_prepare_lane(DevModel m, DevBatch b, double dt) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= b.W) return;
-  world_update_dynamic(m, b, w);
   world_fused_prepare(m, b, w, dt);
 }
 __global__ void __launch_bounds__(FUSED_THREADS) k_fused_gs(DevModel m, DevBatch b, double dt) {
@@ -38,7 +36,8 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_fused_finish(DevModel m, DevB
   if (w < b.W) world_fused_finish(m, b, w, dt);
 }
 
-bool arb_fused_supported(const arb_batch*) { return true; }
+// the fused stages fold controllers per dof: PD gains must be diagonal (arb_model_host.h)
+bool arb_fused_supported(const arb_batch* b) { return b->model->host.fused_ok != 0; }
 
 static int ensure_fused_scratch(arb_batch* b) {
   if (b->fused) return 0;
@@ -58,8 +57,6 @@ static int ensure_fused_scratch(arb_batch* b) {
 
 int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
   int rc = ensure_fused_scratch(b);
-  if (rc) return rc;
-  rc = arb_ensure_phase_scratch(b);
   if (rc) return rc;
   const unsigned g = (unsigned)((b->d.W + FUSED_THREADS - 1) / FUSED_THREADS);
   for (int s = 0; s < nsteps; ++s) {

@@ -1,65 +1,23 @@
 // The fused step, stage by stage.  Same results as the four API phases
 // (core.py:1356-1363) but organised for the GPU:
 //
-//  prepare : kinematics, assembly of Z = M/dt + B + N, gravity/controllers, then instead
-//            of the explicit 42x42 inverse (core.py:818) a no-fill elimination of Z that
-//            exploits the tree sparsity (Z[i][j] != 0 only for dofs on a common root path;
-//            eliminating dofs leaf-to-root creates no fill-in), the unconstrained velocity
-//            q_free = Z^-1 (M q'/dt + g), and the constraint problem reduced to "generator"
-//            space: constraint Jacobians are J_c = T1_c J_body1 - T0_c J_body0, so with
-//            G = stacked body Jacobians of the few bodies that carry constraint frames
-//            (the two feet for human36) only  W = Z^-1 G^T,  Lambda = G W  and v0 = G q_free
-//            are needed:  J_c Y J_d^T = T_c Lambda T_d^T  (core.py:925-927).
+//  prepare : kinematics, then -- instead of assembling M, N, B, Z = M/dt + B + N and the
+//            explicit 42x42 inverse (core.py:722-734, 813-818) -- the articulated-body
+//            elimination of arb_artic.cuh (O(ndof), nothing bigger than a 6x6 block), the
+//            unconstrained velocity q_free = Z^-1 (M q'/dt + g), and the constraint problem
+//            reduced to "generator" space: constraint Jacobians are
+//            J_c = T1_c J_body1 - T0_c J_body0, so with G = stacked body Jacobians of the few
+//            bodies that carry constraint frames (the two feet for human36) plus one unit row
+//            per limited joint, only  Lambda = G Z^-1 G^T  and  v0 = G q_free  are needed:
+//            J_c Y J_d^T = T_c Lambda T_d^T  (core.py:925-927).
 //  gs      : the 20 sequential Gauss-Seidel sweeps (core.py:929-935) in generator space,
 //            one world per lane; u = v0 + Lambda y is kept up to date, y = sum T_c^T f_c.
-//  finish  : q'+ = q_free + W y (equals core.py:975-976) and joint integration.
-//
-// The scalar (lane-per-world) prepare below is the portable implementation and the
-// reference for the warp-per-world kernel in arb_fused.cu; gs and finish are always
-// lane-per-world.
+//  finish  : q'+ = q_free + Z^-1 G^T y (equals core.py:975-976) by one more articulated
+//            solve, and joint integration.
 #pragma once
+#include "arb_artic.cuh"
 #include "arb_constraints.cuh"
 #include "arb_world.cuh"
-
-// ---- no-fill elimination of Z in place (row-major n x n, only structural entries touched)
-// after it: Z[k][k] pivots, Z[anc][k] multipliers (column k above the diagonal, already
-// divided by the pivot), Z[k][anc] the eliminated row.
-ARB_D bool tree_factor(const DevModel& m, double* Z, int64_t W, int64_t w) {
-  const int n = m.ndof;
-  bool ok = true;
-  for (int k = n - 1; k >= 0; --k) {
-    const int a = m.dofpos[k];
-    const int* anc = m.pathdof + m.coloff[m.dofbody[k]];
-    const double d = AT(Z, k * n + k);
-    if (!(fabs(d) > 0.)) ok = false;
-    const double inv = 1. / d;
-    for (int i = 0; i < a; ++i) {
-      const int ai = anc[i];
-      const double l = AT(Z, ai * n + k) * inv;
-      AT(Z, ai * n + k) = l;
-      for (int j = 0; j < a; ++j) AT(Z, ai * n + anc[j]) -= l * AT(Z, k * n + anc[j]);
-    }
-  }
-  return ok;
-}
-// x <- Z^-1 x using the factorisation above
-ARB_D void tree_solve(const DevModel& m, const double* Z, double* x, int64_t W, int64_t w) {
-  const int n = m.ndof;
-  for (int k = n - 1; k >= 0; --k) {
-    const int a = m.dofpos[k];
-    const int* anc = m.pathdof + m.coloff[m.dofbody[k]];
-    const double rk = AT(x, k);
-    if (rk == 0.) continue;
-    for (int i = 0; i < a; ++i) AT(x, anc[i]) -= AT(Z, anc[i] * n + k) * rk;
-  }
-  for (int k = 0; k < n; ++k) {
-    const int a = m.dofpos[k];
-    const int* anc = m.pathdof + m.coloff[m.dofbody[k]];
-    double t = AT(x, k);
-    for (int j = 0; j < a; ++j) t -= AT(Z, k * n + anc[j]) * AT(x, anc[j]);
-    AT(x, k) = t / AT(Z, k * n + k);
-  }
-}
 
 // Per-constraint update from body poses/twists: activation, aux (sdist / pos0 / q) and the
 // maps T1 (from body1's twist) and T0 (from body0's twist) to the constraint rows.
@@ -138,65 +96,13 @@ ARB_D bool constraint_update(const DevModel& m, int c, const Se3& P0, const Se3&
 }
 
 // ---------------------------------------------------------------------------------------
-// prepare, scalar version: runs after world_update_dynamic (uses its scratch).
+// prepare: see the header.  Reads the bound state only; writes the fused scratch.
 ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, double dt) {
   const int64_t W = b.W;
-  const int n = m.ndof, NG = m.ngrows;
-  // controllers: gforce and Z (no inverse)                                 (core.py:812-817)
-  for (int i = 0; i < n; ++i) AT(b.gforce, i) = 0.;
-  for (int i = 0; i < n * n; ++i) AT(b.Z, i) = AT(b.M, i) / dt + AT(b.B, i) + AT(b.N, i);
-  for (int a = 0; a < m.na; ++a) {
-    if (m.atype[a] == ARB_CTRL_WEIGHT) {
-      const double grav = m.adbl[4 * a];
-      double gt[6] = {0., 0., 0., grav * m.up[0], grav * m.up[1], grav * m.up[2]};
-      for (int j = 0; j < m.nj; ++j) {
-        if (!(m.bflags[j] & ARB_BODY_MASSIVE)) continue;
-        Se3 H;
-        load_pose(b, j + 1, w, H);
-        double g[6], wr[6];
-        iad_apply(H, gt, g);
-        const double* Mb = m.bmass + 36 * j;
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          double t = 0.;
-#pragma unroll
-          for (int c = 0; c < 6; ++c) t += Mb[6 * r + c] * g[c];
-          wr[r] = t;
-        }
-        const int off = m.coloff[j + 1], kc = m.kcols[j + 1];
-        for (int l = 0; l < kc; ++l) {
-          double t = 0.;
-#pragma unroll
-          for (int i = 0; i < 6; ++i) t += AT(b.J, (off + l) * 6 + i) * wr[i];
-          AT(b.gforce, m.pathdof[off + l]) += t;
-        }
-      }
-    } else {
-      const int mm = m.aint[4 * a], off = m.aint[4 * a + 1];
-      const double* dofs = m.ablob + off;
-      const double* gmap = dofs + mm;
-      const double* kp = gmap + mm;
-      const double* kd = kp + mm * mm;
-      const double* qd = kd + mm * mm;
-      const double* dqd = qd + mm;
-      for (int i = 0; i < mm; ++i) {
-        double t = 0., t2 = 0.;
-        for (int j = 0; j < mm; ++j) t += kp[i * mm + j] * (qd[j] - AT(b.gpos, (int)gmap[j]));
-        for (int j = 0; j < mm; ++j) t2 += kd[i * mm + j] * dqd[j];
-        AT(b.gforce, (int)dofs[i]) += t + t2;
-        for (int j = 0; j < mm; ++j)
-          AT(b.Z, (int)dofs[i] * n + (int)dofs[j]) -= -(dt * kp[i * mm + j] + kd[i * mm + j]);
-      }
-    }
-  }
-  // rhs = M gvel/dt + gforce ; q_free = Z^-1 rhs
-  for (int i = 0; i < n; ++i) {
-    double t = 0.;
-    for (int j = 0; j < n; ++j) t += AT(b.M, i * n + j) * (AT(b.gvel, j) / dt);
-    AT(b.fq, i) = t + AT(b.gforce, i);
-  }
-  if (!tree_factor(m, b.Z, W, w)) b.status[w] |= ARB_STATUS_SINGULAR;
-  tree_solve(m, b.Z, b.fq, W, w);
+  const int NG = m.ngrows;
+  artic_kinematics(m, b, w);
+  if (!artic_factor(m, b, w, dt)) b.status[w] |= ARB_STATUS_SINGULAR;
+  artic_forward_full<false>(m, b, w, b.au, b.fq);   // q_free
   // constraints: activation, T maps
   bool any = false;
   for (int c = 0; c < m.nc; ++c) {
@@ -217,10 +123,13 @@ ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, 
     } else {
       Se3 P0, P1;
       double TW0[6], TW1[6];
-      load_pose(b, ci[0], w, P0);
-      load_pose(b, ci[1], w, P1);
-      load_twist(b, ci[0], w, TW0);
-      load_twist(b, ci[1], w, TW1);
+      if (ci[0] == 0) se3_identity(P0); else load_se3(b.fpose, ci[0] - 1, W, w, P0);
+      if (ci[1] == 0) se3_identity(P1); else load_se3(b.fpose, ci[1] - 1, W, w, P1);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        TW0[i] = (ci[0] == 0) ? 0. : AT(b.atw, (ci[0] - 1) * 6 + i);
+        TW1[i] = (ci[1] == 0) ? 0. : AT(b.atw, (ci[1] - 1) * 6 + i);
+      }
       act = constraint_update(m, c, P0, P1, TW0, TW1, 0., dt, aux, T1, T0, zi);
       if (type == ARB_CONS_SOFT_FINGER_PLANE_POINT) {
 #pragma unroll
@@ -237,35 +146,17 @@ ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, 
     any = any || act;
   }
   if (!any) return;
-  // generator space: W = Z^-1 G^T, Lambda = G W, v0 = G q_free
-  for (int g = 0; g < NG; ++g) {
-    double* x = b.fW + (int64_t)g * n * W;
-    for (int i = 0; i < n; ++i) AT(x, i) = 0.;
-    if (g < 6 * m.ngen) {
-      const int body = m.gen_body[g / 6], r = g % 6;
-      const int off = m.coloff[body], kc = m.kcols[body];
-      for (int l = 0; l < kc; ++l) AT(x, m.pathdof[off + l]) = AT(b.J, (off + l) * 6 + r);
-    } else {
-      for (int c = 0; c < m.nc; ++c)
-        if (m.ctype[c] == ARB_CONS_JOINT_LIMITS && m.cgen1[c] == g) AT(x, m.cint[ARB_CONS_NINT * c + 1]) = 1.;
-    }
-    tree_solve(m, b.Z, x, W, w);
+  // generator space: v0 = G q_free, Lambda = G Z^-1 G^T (column block by column block)
+  for (int g = 0; g < NG; ++g) AT(b.fv0, g) = artic_gen_value(m, b, w, g, 0, b.fq);
+  for (int gi = 0; gi < m.ngen; ++gi) {
+    artic_solve_generators<6>(m, b, w, m.gen_body[gi], -1);
+    for (int r = 0; r < 6; ++r)
+      for (int g = 0; g < NG; ++g) AT(b.fLam, g * NG + 6 * gi + r) = artic_gen_value(m, b, w, g, r, b.ax);
   }
-  for (int g = 0; g < NG; ++g) {
-    // row g of G applied to a dof-vector
-    for (int h = 0; h <= NG; ++h) {
-      const double* x = (h < NG) ? b.fW + (int64_t)h * n * W : b.fq;
-      double t = 0.;
-      if (g < 6 * m.ngen) {
-        const int body = m.gen_body[g / 6], r = g % 6;
-        const int off = m.coloff[body], kc = m.kcols[body];
-        for (int l = 0; l < kc; ++l) t += AT(b.J, (off + l) * 6 + r) * AT(x, m.pathdof[off + l]);
-      } else {
-        for (int c = 0; c < m.nc; ++c)
-          if (m.ctype[c] == ARB_CONS_JOINT_LIMITS && m.cgen1[c] == g) t = AT(x, m.cint[ARB_CONS_NINT * c + 1]);
-      }
-      if (h < NG) AT(b.fLam, g * NG + h) = t; else AT(b.fv0, g) = t;
-    }
+  for (int h = 6 * m.ngen; h < NG; ++h) {
+    const int k = m.glimdof[h - 6 * m.ngen];
+    artic_solve_generators<1>(m, b, w, m.dofbody[k], k);
+    for (int g = 0; g < NG; ++g) AT(b.fLam, g * NG + h) = artic_gen_value(m, b, w, g, 0, b.ax);
   }
 }
 
@@ -439,17 +330,18 @@ ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, doubl
 // ---------------------------------------------------------------------------------------
 ARB_D void world_fused_finish(const DevModel& m, const DevBatch& b, int64_t w, double dt) {
   const int64_t W = b.W;
-  const int n = m.ndof, NG = m.ngrows;
+  const int n = m.ndof;
   bool any = false;
   for (int c = 0; c < m.nc; ++c) any = any || AT(b.factive, c);
+  // q'+ = q_free + Z^-1 G^T y
+  if (any) {
+    artic_backward_wrenches(m, b, w, b.fy);
+    artic_forward_full<true>(m, b, w, b.au, b.ax);
+  }
   bool finite = true;
   for (int i = 0; i < n; ++i) {
     double t = AT(b.fq, i);
-    if (any)
-      for (int g = 0; g < NG; ++g) {
-        const double yg = AT(b.fy, g);
-        if (yg != 0.) t += AT(b.fW, (int64_t)g * n + i) * yg;
-      }
+    if (any) t += AT(b.ax, i);
     AT(b.gvel, i) = t;
     finite = finite && isfinite(t);
   }

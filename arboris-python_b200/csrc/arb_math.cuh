@@ -90,6 +90,14 @@ ARB_HD void se3_from16(const double* m, Se3& h) {
   }
 }
 
+// frame j of a table of constant frames stored as 12 doubles (R row-major, p)
+ARB_HD void load_se3_const(const double* tab, int j, Se3& h) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) h.R[i] = tab[12 * j + i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) h.p[i] = tab[12 * j + 9 + i];
+}
+
 // y = Ad(H) x,  Ad = [[R,0],[p^ R, R]]   (homogeneousmatrix.py:308-319)
 ARB_HD void ad_apply(const Se3& h, const double* x, double* y) {
   double rw[3], rv[3], c[3];

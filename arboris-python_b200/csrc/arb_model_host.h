@@ -15,6 +15,13 @@ struct HostModel {
   std::vector<int> ctype, cint, crow, atype, aint;
   std::vector<int> dofbody, dofpos, gen_body, cgen1, cgen0;
   int ngen = 0, ngrows = 0;
+  // articulated-body tables
+  std::vector<int> dofjoint, jhaschild, jaccfirst, jmark, jmarkfirst, jmarkchild, glimdof, pd_gpos;
+  std::vector<double> pd_kp, pd_kd, pd_qd, pd_c;
+  int has_pd = 0, nweight = 0;
+  double gravity = 0.;
+  int fused_ok = 1;            // 0: a controller couples dofs in a way the fused step does not support
+  std::string fused_why;
   std::vector<double> Hpr, HprInv, Hcn, HcnInv, bmass, bvisc, brx, cdbl, adbl, ablob;
   double up[3] = {0., 1., 0.};
 };
@@ -141,7 +148,63 @@ static inline int build_host_model(const arb_model_desc* d, HostModel& m, std::s
   m.ngen = (int)m.gen_body.size();
   m.ngrows = 6 * m.ngen;
   for (int c = 0; c < m.nc; ++c)
-    if (m.ctype[c] == ARB_CONS_JOINT_LIMITS) m.cgen1[c] = m.ngrows++;
+    if (m.ctype[c] == ARB_CONS_JOINT_LIMITS) {
+      m.cgen1[c] = m.ngrows++;
+      m.glimdof.push_back(m.cint[ARB_CONS_NINT * c + 1]);
+    }
+  // articulated-body tables: tree shape, generator paths, controllers folded per dof
+  m.dofjoint.assign(m.ndof, 0);
+  for (int k = 0; k < m.ndof; ++k) m.dofjoint[k] = m.dofbody[k] - 1;
+  m.jhaschild.assign(nj, 0); m.jaccfirst.assign(nj, 0);
+  m.jmark.assign(nj, 0); m.jmarkfirst.assign(nj, 0); m.jmarkchild.assign(nj, 0);
+  {
+    std::vector<int> seen(nj + 1, 0);
+    for (int j = nj - 1; j >= 0; --j) {
+      const int p = m.jparent[j];
+      if (p == 0) continue;
+      m.jhaschild[p - 1] = 1;
+      if (!seen[p]) { seen[p] = 1; m.jaccfirst[j] = 1; }
+    }
+    auto mark_path = [&](int body) {
+      while (body > 0) { m.jmark[body - 1] = 1; body = m.jparent[body - 1]; }
+    };
+    for (int g = 0; g < m.ngen; ++g) mark_path(m.gen_body[g]);
+    for (size_t i = 0; i < m.glimdof.size(); ++i) mark_path(m.dofbody[m.glimdof[i]]);
+    std::vector<int> seenm(nj + 1, 0);
+    for (int j = nj - 1; j >= 0; --j) {
+      const int p = m.jparent[j];
+      if (p == 0 || !m.jmark[j]) continue;
+      m.jmarkchild[p - 1] = 1;
+      if (!seenm[p]) { seenm[p] = 1; m.jmarkfirst[j] = 1; }
+    }
+  }
+  m.pd_kp.assign(m.ndof, 0.); m.pd_kd.assign(m.ndof, 0.); m.pd_qd.assign(m.ndof, 0.);
+  m.pd_c.assign(m.ndof, 0.); m.pd_gpos.assign(m.ndof, -1);
+  for (int a = 0; a < m.na; ++a) {
+    if (m.atype[a] == ARB_CTRL_WEIGHT) { m.gravity += m.adbl[4 * a]; m.nweight++; continue; }
+    m.has_pd = 1;
+    const int mm = m.aint[4 * a], off = m.aint[4 * a + 1];
+    const double* dofs = &m.ablob[off];
+    const double* gmap = dofs + mm;
+    const double* kp = gmap + mm;
+    const double* kd = kp + mm * mm;
+    const double* qd = kd + mm * mm;
+    const double* dqd = qd + mm;
+    for (int i = 0; i < mm; ++i) {
+      const int k = (int)dofs[i];
+      for (int j = 0; j < mm; ++j)
+        if (i != j && (kp[i * mm + j] != 0. || kd[i * mm + j] != 0.)) {
+          m.fused_ok = 0;
+          m.fused_why = "PD controller with off-diagonal gains";
+        }
+      if (m.pd_gpos[k] >= 0) { m.fused_ok = 0; m.fused_why = "two PD controllers on one dof"; }
+      m.pd_gpos[k] = (int)gmap[i];
+      m.pd_kp[k] = kp[i * mm + i];
+      m.pd_kd[k] = kd[i * mm + i];
+      m.pd_qd[k] = qd[i];
+      m.pd_c[k] = kd[i * mm + i] * dqd[i];
+    }
+  }
   return 0;
 }
 
@@ -166,25 +229,37 @@ static inline ScratchSizes scratch_sizes(const HostModel& m) {
   return s;
 }
 struct FusedSizes {
-  int64_t fq, fW, fLam, fv0, fT1, fT0, fu, fy, fAcc, fP, faux, fpose, factive, fbranch;
-  int64_t total_doubles() const { return fq + fW + fLam + fv0 + fT1 + fT0 + fu + fy + fAcc + fP + faux + fpose; }
+  int64_t fq, fLam, fv0, fT1, fT0, fu, fy, fAcc, fP, faux, fpose, factive, fbranch;
+  int64_t aX, atw, ath, aS, aSh, aU, aLA, aLM, adinv, aIA, aIM, abeta, au, ax, aV;
+  int64_t total_doubles() const {
+    return fq + fLam + fv0 + fT1 + fT0 + fu + fy + fAcc + fP + faux + fpose +
+           aX + atw + ath + aS + aSh + aU + aLA + aLM + adinv + aIA + aIM + abeta + au + ax + aV;
+  }
   int64_t total_ints() const { return factive + fbranch; }
 };
 static inline FusedSizes fused_sizes(const HostModel& m) {
   FusedSizes s;
   const int64_t n = m.ndof, NG = m.ngrows > 0 ? m.ngrows : 1, nc = m.nc > 0 ? m.nc : 1,
                 nr = m.nrows > 0 ? m.nrows : 1;
-  s.fq = n; s.fW = NG * n; s.fLam = NG * NG; s.fv0 = NG; s.fT1 = nc * 24; s.fT0 = nc * 24;
-  s.fu = NG; s.fy = NG; s.fAcc = nr * 4; s.fP = nr * 4; s.faux = nc * 4; s.fpose = (int64_t)m.nj * 12;
+  const int64_t nj = m.nj > 0 ? m.nj : 1, nn = n > 0 ? n : 1;
+  s.fq = nn; s.fLam = NG * NG; s.fv0 = NG; s.fT1 = nc * 24; s.fT0 = nc * 24;
+  s.fu = NG; s.fy = NG; s.fAcc = nr * 4; s.fP = nr * 4; s.faux = nc * 4; s.fpose = nj * 12;
   s.factive = nc; s.fbranch = nc;
+  s.aX = nj * 12; s.atw = nj * 6; s.ath = nj * 6;
+  s.aS = s.aSh = s.aU = s.aLA = s.aLM = nn * 6; s.adinv = nn;
+  s.aIA = s.aIM = nj * 36; s.abeta = nj * 6; s.au = 6 * nn; s.ax = 6 * nn; s.aV = nj * 72;
   return s;
 }
 static inline void carve_fused(const FusedSizes& s, int64_t W, double* dbl, int* ints, DevBatch& b) {
   double* p = dbl;
   auto take = [&](int64_t k) { double* r = p; p += k * W; return r; };
-  b.fq = take(s.fq); b.fW = take(s.fW); b.fLam = take(s.fLam); b.fv0 = take(s.fv0);
+  b.fq = take(s.fq); b.fLam = take(s.fLam); b.fv0 = take(s.fv0);
   b.fT1 = take(s.fT1); b.fT0 = take(s.fT0); b.fu = take(s.fu); b.fy = take(s.fy);
   b.fAcc = take(s.fAcc); b.fP = take(s.fP); b.faux = take(s.faux); b.fpose = take(s.fpose);
+  b.aX = take(s.aX); b.atw = take(s.atw); b.ath = take(s.ath);
+  b.aS = take(s.aS); b.aSh = take(s.aSh); b.aU = take(s.aU); b.aLA = take(s.aLA); b.aLM = take(s.aLM);
+  b.adinv = take(s.adinv); b.aIA = take(s.aIA); b.aIM = take(s.aIM); b.abeta = take(s.abeta);
+  b.au = take(s.au); b.ax = take(s.ax); b.aV = take(s.aV);
   int* q = ints;
   auto takei = [&](int64_t k) { int* r = q; q += k * W; return r; };
   b.factive = takei(s.factive); b.fbranch = takei(s.fbranch);

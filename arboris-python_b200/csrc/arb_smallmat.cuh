@@ -286,3 +286,177 @@ ARB_NOINLINE bool eig_real_general6(double* a, double* wr, double* wi) {
 #undef A_
   return ok;
 }
+
+// ---- smallest real eigenvalue <= 0 of the sliding-friction matrix, structured ---------------
+// The matrix of constraints.py:815-821 (with eps = (1,1,1), the value the reference fixes at
+// constraints.py:423) is  B = [[Q + c J, al I], [ga I, Q]]  with J the all-ones 3x3 matrix.
+// Its lower-left block commutes with everything, so
+//     det(B - s I) = det( (Q + c J - s I)(Q - s I) - al ga I )  = det( s^2 I - s C1 + C0 ),
+// a 3x3 quadratic matrix polynomial.  With s = -sigma t the wanted root (min real s <= 0,
+// constraints.py:825-830) is the LARGEST real root t >= 0 of a monic sextic.  Real roots are
+// isolated by derivative interlacing (between two consecutive real roots of p' the polynomial
+// p is monotone), each bracket refined by safeguarded Newton, and the result polished by
+// Newton on the 3x3 determinant itself (not on the expanded coefficients).  Control flow is
+// data independent apart from iteration counts -- unlike a shifted QR iteration, lanes of a
+// warp do not diverge.  eig_real_general6 above stays as the general path.
+template <int D>
+ARB_HD double poly_val(const double* c, double x) {
+  double f = c[D];
+#pragma unroll
+  for (int k = D - 1; k >= 0; --k) f = f * x + c[k];
+  return f;
+}
+// root of c in (lo, hi) given f(lo) = flo != 0 and a sign change on the bracket
+template <int D>
+ARB_HD double poly_refine(const double* c, double lo, double hi, double flo) {
+  double x = 0.5 * (lo + hi);
+  const bool lo_neg = flo < 0.;
+  for (int it = 0; it < 200; ++it) {
+    double f = c[D], df = 0.;
+#pragma unroll
+    for (int k = D - 1; k >= 0; --k) { df = df * x + f; f = f * x + c[k]; }
+    if (f == 0.) break;
+    if ((f < 0.) == lo_neg) lo = x; else hi = x;
+    double xn = x - f / df;
+    if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
+    if (xn == x || !(hi - lo > 0.)) break;
+    const bool done = fabs(xn - x) <= 4e-16 * fabs(xn);
+    x = xn;
+    if (done) break;
+  }
+  return x;
+}
+// real roots in [0, T] of the degree-D polynomial c[0..D] (c[D] != 0), ascending; returns count
+template <int D>
+struct PolyRoots {
+  static ARB_HD int run(const double* c, double T, double* roots) {
+    double dc[D], crit[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) dc[k] = (k + 1) * c[k + 1];
+    const int nc = PolyRoots<D - 1>::run(dc, T, crit);
+    int n = 0;
+    double lo = 0., flo = c[0];
+    if (flo == 0.) roots[n++] = 0.;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      if (i <= nc) {
+        const double hi = (i < nc) ? crit[i] : T;
+        const double fhi = poly_val<D>(c, hi);
+        if ((flo < 0. && fhi > 0.) || (flo > 0. && fhi < 0.)) roots[n++] = poly_refine<D>(c, lo, hi, flo);
+        else if (fhi == 0. && hi > lo) roots[n++] = hi;
+        lo = hi;
+        flo = fhi;
+      }
+    }
+    return n;
+  }
+};
+template <>
+struct PolyRoots<1> {
+  static ARB_HD int run(const double* c, double T, double* roots) {
+    const double x = -c[0] / c[1];
+    if (x >= 0. && x <= T) { roots[0] = x; return 1; }
+    return 0;
+  }
+};
+
+// A: 4x4 contact admittance block, alpha: the vector of constraints.py:807-808, mu: friction.
+// Returns false if the structured path does not apply (caller falls back to the general
+// eigenvalue routine); else *found tells whether a real eigenvalue <= 0 exists and *s_out is it.
+ARB_HD bool sliding_root_structured(const double* A, const double* alpha, double mu, double* s_out, bool* found) {
+  const double Yc[3] = {A[3], A[7], A[11]};
+  const double yn = A[15];
+  const double a = mu / yn * alpha[3];
+  double beta[3], bb[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    beta[i] = alpha[i] - alpha[3] / yn * Yc[i];
+    bb[i] = mu / yn * Yc[i];
+  }
+  const double kappa = (Yc[0] * Yc[0] + Yc[1] * Yc[1] + Yc[2] * Yc[2]) / yn;
+  const double cc = 2. / a * (beta[0] * bb[0] + beta[1] * bb[1] + beta[2] * bb[2]);
+  const double al = -((beta[0] * beta[0] + beta[1] * beta[1] + beta[2] * beta[2]) / (a * a));
+  const double ga = (bb[0] * bb[0] + bb[1] * bb[1] + bb[2] * bb[2]) - 1.;
+  const double delta = al * ga;
+  double Q[9];
+  double sigma = sqrt(fabs(delta));
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      Q[3 * i + j] = A[4 * i + j] - kappa;
+      sigma = fmax(sigma, fabs(Q[3 * i + j]) + fabs(cc));
+    }
+  if (!(sigma > 0.) || !(sigma < 1e300)) return false;
+  // scaled coefficients of  M(t) = t^2 I + t C1 + C0,  s = -sigma t
+  const double is = 1. / sigma;
+  double C1[9], C0[9];
+  const double cs[3] = {Q[0] + Q[3] + Q[6], Q[1] + Q[4] + Q[7], Q[2] + Q[5] + Q[8]};  // J Q rows
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      C1[3 * i + j] = (2. * Q[3 * i + j] + cc) * is;
+      double t = Q[3 * i] * Q[j] + Q[3 * i + 1] * Q[3 + j] + Q[3 * i + 2] * Q[6 + j] + cc * cs[j];
+      if (i == j) t -= delta;
+      C0[3 * i + j] = t * is * is;
+    }
+  // sextic p(t) = det M(t): entries m_ij(t) = d_ij t^2 + C1_ij t + C0_ij
+  double p[7] = {0., 0., 0., 0., 0., 0., 0.};
+  {
+    // 2x2 minors of rows 1,2 as quartics, then expand along row 0
+#define ARB_QUAD(i, j, q) { (q)[0] = C0[3 * (i) + (j)]; (q)[1] = C1[3 * (i) + (j)]; (q)[2] = ((i) == (j)) ? 1. : 0.; }
+    const int cols[3][2] = {{1, 2}, {0, 2}, {0, 1}};
+#pragma unroll
+    for (int e = 0; e < 3; ++e) {
+      double u[3], v[3], x[3], y[3], mnr[5] = {0., 0., 0., 0., 0.};
+      ARB_QUAD(1, cols[e][0], u); ARB_QUAD(2, cols[e][1], v); ARB_QUAD(1, cols[e][1], x); ARB_QUAD(2, cols[e][0], y);
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) mnr[i + j] += u[i] * v[j] - x[i] * y[j];
+      double r0[3];
+      ARB_QUAD(0, e, r0);
+      const double sgn = (e == 1) ? -1. : 1.;
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) p[i + j] += sgn * r0[i] * mnr[j];
+    }
+#undef ARB_QUAD
+  }
+  if (!(fabs(p[6] - 1.) < 1e-9)) return false;
+  p[6] = 1.;
+  double T = 0.;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) T = fmax(T, fabs(p[k]));
+  T += 1.;
+  if (!(T < 1e300)) return false;
+  double roots[6];
+  const int nr = PolyRoots<6>::run(p, T, roots);
+  if (nr == 0) { *found = false; *s_out = 0.; return true; }
+  double t = roots[nr - 1];
+  // polish on det M(t):  f' = tr(adj(M) (2 t I + C1))
+  for (int it = 0; it < 3; ++it) {
+    double M[9], dM[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const double id = (i % 4 == 0) ? 1. : 0.;
+      M[i] = (id * t + C1[i]) * t + C0[i];
+      dM[i] = 2. * id * t + C1[i];
+    }
+    const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+    const double c10 = M[2] * M[7] - M[1] * M[8], c11 = M[0] * M[8] - M[2] * M[6], c12 = M[1] * M[6] - M[0] * M[7];
+    const double c20 = M[1] * M[5] - M[2] * M[4], c21 = M[2] * M[3] - M[0] * M[5], c22 = M[0] * M[4] - M[1] * M[3];
+    const double f = M[0] * c00 + M[1] * c01 + M[2] * c02;
+    // adj(M)_ji = cofactor_ij ;  tr(adj(M) dM) = sum_ij cof_ij dM_ij
+    const double df = c00 * dM[0] + c01 * dM[1] + c02 * dM[2] + c10 * dM[3] + c11 * dM[4] + c12 * dM[5] +
+                      c20 * dM[6] + c21 * dM[7] + c22 * dM[8];
+    const double tn = t - f / df;
+    if (!(fabs(tn - t) <= 1e-6 * (fabs(t) + 1e-6)) || tn < 0.) break;   // not a simple, well-isolated root
+    t = tn;
+  }
+  *found = true;
+  *s_out = -sigma * t;
+  return true;
+}

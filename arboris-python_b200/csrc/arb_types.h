@@ -52,6 +52,20 @@ struct DevModel {
   int ngen, ngrows;                            // generator bodies, total rows NG
   const int *gen_body;                         // [ngen]
   const int *cgen1, *cgen0;                    // [nc] first generator row of body1 / body0 (or -1)
+  // ---- articulated-body tables (arb_artic.cuh) -----------------------------------------
+  const int *dofjoint;                         // [ndof] joint of each dof
+  const int *jhaschild;                        // [nj] body j+1 has child joints
+  const int *jaccfirst;                        // [nj] joint j is the highest-numbered child of its parent body
+  const int *jmark;                            // [nj] body j+1 lies on the root path of a generator
+  const int *jmarkfirst;                       // [nj] highest-numbered MARKED child of its parent body
+  const int *jmarkchild;                       // [nj] body j+1 has marked child joints
+  const int *glimdof;                          // [ngrows - 6 ngen] dof of each joint-limit generator row
+  // diagonal PD controllers folded per dof: tau = kp (qd - q) + c, Z[k][k] += dt kp + kd
+  int has_pd;
+  const double *pd_kp, *pd_kd, *pd_qd, *pd_c;  // [ndof]
+  const int *pd_gpos;                          // [ndof] gpos index of the dof (or -1)
+  double gravity;                              // sum of the WeightControllers' gravity
+  int nweight;
 };
 
 // Per-batch memory: caller-owned state + library-owned scratch, all [elem][W].
@@ -79,7 +93,6 @@ struct DevBatch {
   // ---- fused path (arb_fused.cuh): what the prepare stage hands to the Gauss-Seidel
   // and finish stages, [elem][W] ------------------------------------------------------
   double *fq;        // [n]        velocity without constraint forces  Z^-1 (M gvel/dt + gforce)
-  double *fW;        // [NG][n]    Z^-1 G^T, one n-vector per generator row
   double *fLam;      // [NG][NG]   G Z^-1 G^T
   double *fv0;       // [NG]       G fq
   double *fT1, *fT0; // [nc][24]   d_c x 6 maps from the body twists to the constraint rows
@@ -88,4 +101,15 @@ struct DevBatch {
   double *faux;      // [nc][4]
   double *fpose;     // [nj][12]   body poses (for contacts and gravity)
   int *factive, *fbranch;  // [nc]
+  // ---- articulated-body factorisation of Z (arb_artic.cuh), [elem][W] ------------------
+  double *aX;        // [nj][12]   H_pc of each joint
+  double *atw, *ath; // [nj][6]    body twist T_b and the accumulated joint term theta_b
+  double *aS, *aSh;  // [n][6]     joint axis s_k in the child body frame and s^_k = ds_k - ad(theta) s_k
+  double *aU, *aLA, *aLM;  // [n][6]  U_k = IA s_k + IM s^_k ; rows s_k^T IA / d_k, s_k^T IM / d_k
+  double *adinv;     // [n]        1 / d_k,  d_k = s_k^T U_k (+ PD diagonal)
+  double *aIA, *aIM; // [nj][36]   children's contributions to the articulated matrices of body j+1
+  double *abeta;     // [nj][6]    children's contributions to the bias wrench
+  double *au;        // [6][n]     reduced right-hand sides u_k, up to 6 at once
+  double *ax;        // [6][n]     solutions
+  double *aV;        // [nj][72]   (V, V^) of each body for up to 6 right-hand sides
 };

@@ -32,12 +32,6 @@ ARB_D void load_twist(const DevBatch& b, int body, int64_t w, double* t) {
 #pragma unroll
   for (int i = 0; i < 6; ++i) t[i] = (body == 0) ? 0. : AT(b.twist, (body - 1) * 6 + i);
 }
-ARB_D void load_se3_const(const double* tab, int j, Se3& h) {
-#pragma unroll
-  for (int i = 0; i < 9; ++i) h.R[i] = tab[12 * j + i];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) h.p[i] = tab[12 * j + 9 + i];
-}
 
 // ---------------------------------------------------------------------------
 ARB_D void world_update_dynamic(const DevModel& m, const DevBatch& b, int64_t w) {

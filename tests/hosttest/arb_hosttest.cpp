@@ -24,6 +24,11 @@ static DevModel view(const HostModel& h) {
   for (int i = 0; i < 3; ++i) m.up[i] = h.up[i];
   m.dofbody = h.dofbody.data(); m.dofpos = h.dofpos.data(); m.ngen = h.ngen; m.ngrows = h.ngrows;
   m.gen_body = h.gen_body.data(); m.cgen1 = h.cgen1.data(); m.cgen0 = h.cgen0.data();
+  m.dofjoint = h.dofjoint.data(); m.jhaschild = h.jhaschild.data(); m.jaccfirst = h.jaccfirst.data();
+  m.jmark = h.jmark.data(); m.jmarkfirst = h.jmarkfirst.data(); m.jmarkchild = h.jmarkchild.data();
+  m.glimdof = h.glimdof.data(); m.pd_gpos = h.pd_gpos.data(); m.pd_kp = h.pd_kp.data();
+  m.pd_kd = h.pd_kd.data(); m.pd_qd = h.pd_qd.data(); m.pd_c = h.pd_c.data();
+  m.has_pd = h.has_pd; m.gravity = h.gravity; m.nweight = h.nweight;
   return m;
 }
 
@@ -84,7 +89,6 @@ void ht_integrate(void* p, double dt) {
 void ht_fused_step(void* p, double dt) {
   HostBatch* hb = (HostBatch*)p;
   for (int64_t w = 0; w < hb->b.W; ++w) {
-    world_update_dynamic(hb->dm, hb->b, w);
     world_fused_prepare(hb->dm, hb->b, w, dt);
     world_fused_gs(hb->dm, hb->b, w, dt);
     world_fused_finish(hb->dm, hb->b, w, dt);
@@ -121,6 +125,13 @@ int ht_eig6(const double* a, double* wr, double* wi) {
   double tmp[36];
   memcpy(tmp, a, sizeof(tmp));
   return eig_real_general6(tmp, wr, wi) ? 1 : 0;
+}
+// structured sliding root: returns 1 if the structured path applied
+int ht_sliding_root(const double* A, const double* alpha, double mu, double* s, int* found) {
+  bool f = false;
+  bool ok = sliding_root_structured(A, alpha, mu, s, &f);
+  *found = f ? 1 : 0;
+  return ok ? 1 : 0;
 }
 int ht_solve4(const double* a, const double* b, double* x) { return solve_small<4>(a, b, x) ? 1 : 0; }
 void ht_exp(const double* tw, double* out12) {

@@ -160,3 +160,51 @@ def test_fused_algorithm_vs_real_reference(name, tol):
     assert not hb.iarr("status").any()
     for k, v in worst.items():
         assert v <= tol, (k, v)
+
+
+def _sliding_matrix(A, alpha, mu):
+    """B of SoftFingerContact.solve exactly as the reference builds it (constraints.py:807-821,
+    eps = 1): note the scalar inner products."""
+    Y_c, y_n, Y_t = A[0:3, 3], A[3, 3], A[0:3, 0:3]
+    beta = alpha[0:3] - alpha[3]/y_n*Y_c
+    a = mu/y_n*alpha[3]
+    b = mu/y_n*Y_c
+    B = np.zeros((6, 6))
+    E = np.eye(3)
+    Y_that = Y_t - np.dot(Y_c, Y_c.T)/y_n
+    B[3:6, 3:6] = np.dot(E, Y_that)
+    B[0:3, 0:3] = np.dot(E, Y_that + 2/a*np.dot(beta, b.T))
+    B[0:3, 3:6] = -np.dot(E, np.dot(beta, beta.T)/(a**2))
+    B[3:6, 0:3] = np.dot(E, np.dot(b, b.T)) - np.eye(3)
+    return B
+
+
+def test_structured_sliding_root_vs_numpy_eigvals():
+    """The structured replacement of eigvals() in the sliding branch (constraints.py:825-830):
+    same admissible root as LAPACK on admittance-like blocks over several scales."""
+    L = harness.lib()
+    dp = C.POINTER(C.c_double)
+    L.ht_sliding_root.argtypes = [dp, dp, C.c_double, dp, C.POINTER(C.c_int)]
+    rng = np.random.default_rng(7)
+    nfound = nnone = 0
+    for trial in range(2000):
+        G = rng.normal(size=(4, 6))
+        A = G.dot(G.T)*10.**rng.uniform(-4, 1)                 # SPD like J Y J^T
+        A = A + rng.normal(size=(4, 4))*1e-2*np.abs(A).max()   # the N term makes it non-symmetric
+        alpha = rng.normal(size=4)*10.**rng.uniform(-3, 1)
+        mu = rng.uniform(0.1, 1.5)
+        S = np.linalg.eigvals(_sliding_matrix(A, alpha, mu))
+        S = S[np.logical_and(S.imag == 0, S.real <= 0)]
+        s, found = C.c_double(0.), C.c_int(0)
+        ok = L.ht_sliding_root(np.ascontiguousarray(A).ctypes.data_as(dp), alpha.ctypes.data_as(dp), mu,
+                               C.byref(s), C.byref(found))
+        assert ok
+        if len(S) == 0:
+            nnone += 1
+            assert not found.value, (trial, s.value)
+        else:
+            nfound += 1
+            ref = float(min(S).real)
+            assert found.value, (trial, ref)
+            assert abs(s.value - ref) <= 1e-9*abs(ref) + 1e-13*np.abs(A).max(), (trial, s.value, ref)
+    assert nfound > 500 and nnone > 10
