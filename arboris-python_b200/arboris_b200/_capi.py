@@ -94,6 +94,7 @@ SYMBOLS = [
     ("arb_get_constraint", _i32, [_vp, _i32, _vp, _i64, _i64]),
     ("arb_batch_status", _i32, [_vp, _vp]),
     ("arb_batch_launch_count", _i64, [_vp]),
+    ("arb_batch_stage_ms", _i32, [_vp, c_dblp]),
     ("arb_measure_fp64_peak", _i32, [_i32, c_dblp]),
 ]
 

@@ -74,7 +74,7 @@ class BatchedWorld(object):
         self._lib.arb_batch_set_stream(self._batch_h, C.c_void_p(s.cuda_stream))
 
     def set_option(self, name, value):
-        """``force_phases`` / ``prepare_warp`` switches of ``arb_batch_set_option``."""
+        """``force_phases`` / ``time_stages`` switches of ``arb_batch_set_option``."""
         _capi.check(self._lib, self._lib.arb_batch_set_option(
             self._batch_h, name.encode(), int(value)))
 
@@ -220,6 +220,13 @@ class BatchedWorld(object):
         self._sync_stream()
         _capi.check(self._lib, self._lib.arb_batch_status(self._batch_h, out.data_ptr()))
         return out
+
+    def stage_ms(self):
+        """{prepare, gs, finish} device milliseconds accumulated since
+        ``set_option("time_stages", 1)`` and the number of steps they cover."""
+        out = (C.c_double*4)()
+        _capi.check(self._lib, self._lib.arb_batch_stage_ms(self._batch_h, out))
+        return {"prepare": out[0], "gs": out[1], "finish": out[2], "steps": int(out[3])}
 
     def launch_count(self):
         return int(self._lib.arb_batch_launch_count(self._batch_h))

@@ -166,6 +166,10 @@ extern "C" int arb_batch_set_option(arb_batch* b, const char* name, int value) {
   const std::string s(name);
   if (s == "force_phases") b->force_phases = value;
   else if (s == "prepare_warp") b->prepare_warp = value;
+  else if (s == "time_stages") {
+    b->time_stages = value;
+    for (int i = 0; i < 4; ++i) b->stage_ms[i] = 0.;
+  }
   else { arb_set_error("unknown option " + s); return -1; }
   return 0;
 }
@@ -450,6 +454,12 @@ extern "C" int arb_batch_status(arb_batch* b, int32_t* flags) {
 }
 
 extern "C" int64_t arb_batch_launch_count(const arb_batch* b) { return b ? b->launches : 0; }
+
+extern "C" int arb_batch_stage_ms(const arb_batch* b, double* out4) {
+  if (!b || !out4) { arb_set_error("null argument"); return -1; }
+  for (int i = 0; i < 4; ++i) out4[i] = b->stage_ms[i];
+  return 0;
+}
 
 // ---------------------------------------------------------------------------------
 // fp64 FMA peak micro-benchmark (roofline denominator; MEASURED_PEAKS.json has no fp64 entry)

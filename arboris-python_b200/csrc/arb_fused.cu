@@ -59,14 +59,32 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
   int rc = ensure_fused_scratch(b);
   if (rc) return rc;
   const unsigned g = (unsigned)((b->d.W + FUSED_THREADS - 1) / FUSED_THREADS);
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (b->time_stages)
+    for (int i = 0; i < 4; ++i) CUDA_OKF(cudaEventCreate(&ev[i]));
   for (int s = 0; s < nsteps; ++s) {
     const double dt = dts[s];
     if (!(dt > 0)) { arb_set_error("dt must be > 0"); return -3; }
+    if (ev[0]) cudaEventRecord(ev[0], b->stream);
     k_fused_prepare_lane<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    if (ev[0]) cudaEventRecord(ev[1], b->stream);
     if (b->m.nc > 0) k_fused_gs<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    if (ev[0]) cudaEventRecord(ev[2], b->stream);
     k_fused_finish<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
     b->launches += (b->m.nc > 0) ? 3 : 2;
+    if (ev[0]) {   // diagnostic mode: per-stage device time of this step
+      cudaEventRecord(ev[3], b->stream);
+      CUDA_OKF(cudaEventSynchronize(ev[3]));
+      for (int i = 0; i < 3; ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+        b->stage_ms[i] += ms;
+      }
+      b->stage_ms[3] += 1.;
+    }
   }
+  for (int i = 0; i < 4; ++i)
+    if (ev[i]) cudaEventDestroy(ev[i]);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { arb_set_error(std::string("kernel launch: ") + cudaGetErrorString(e)); return -101; }
   return 0;

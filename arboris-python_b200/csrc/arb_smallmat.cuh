@@ -10,12 +10,70 @@
 #include "arb_math.cuh"
 
 // ---- Moore-Penrose pseudo-inverse of an n x n matrix, n <= 4 (row-major) -----
+// Inverse by Gauss-Jordan elimination with partial pivoting; returns the 1-norm condition
+// number ||A||_1 ||A^-1||_1 (inf when a pivot vanishes).
+template <int N>
+ARB_D double inv_small_cond(const double* a_in, double* out) {
+  double a[N * N], x[N * N];
+  double an = 0.;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double c = 0.;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { a[i * N + j] = a_in[i * N + j]; x[i * N + j] = (i == j) ? 1. : 0.; c += fabs(a_in[i * N + j]); }
+    an = fmax(an, c);
+  }
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    int piv = k;
+    double best = fabs(a[k * N + k]);
+#pragma unroll
+    for (int i = k + 1; i < N; ++i)
+      if (fabs(a[i * N + k]) > best) { best = fabs(a[i * N + k]); piv = i; }
+    if (!(best > 0.)) ok = false;
+#pragma unroll
+    for (int i = k + 1; i < N; ++i)
+      if (i == piv) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          double t = a[k * N + j]; a[k * N + j] = a[i * N + j]; a[i * N + j] = t;
+          t = x[k * N + j]; x[k * N + j] = x[i * N + j]; x[i * N + j] = t;
+        }
+      }
+    const double inv = 1. / a[k * N + k];
+#pragma unroll
+    for (int j = 0; j < N; ++j) { a[k * N + j] *= inv; x[k * N + j] *= inv; }
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (i != k) {
+        const double f = a[i * N + k];
+#pragma unroll
+        for (int j = 0; j < N; ++j) { a[i * N + j] -= f * a[k * N + j]; x[i * N + j] -= f * x[k * N + j]; }
+      }
+  }
+  double xn = 0.;
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double c = 0.;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { out[i * N + j] = x[i * N + j]; c += fabs(x[i * N + j]); }
+    xn = fmax(xn, c);
+  }
+  const double cond = an * xn;
+  return (ok && cond == cond) ? cond : 1e300;
+}
+
 template <int N>
 ARB_D void pinv_small(const double* a, double* out) {
   if (N == 1) {
     out[0] = (a[0] != 0.) ? 1. / a[0] : 0.;
     return;
   }
+  // numpy.linalg.pinv zeroes singular values below 1e-15 sigma_max.  cond_2 <= N cond_1, so a
+  // block with cond_1 < 1e12 loses no singular value and its pseudo-inverse IS its inverse:
+  // take the elimination result and leave the SVD to the (near-)singular blocks.
+  if (inv_small_cond<N>(a, out) < 1e12) return;
   double U[N * N], V[N * N];
 #pragma unroll
   for (int i = 0; i < N * N; ++i) { U[i] = a[i]; V[i] = ((i % (N + 1)) == 0) ? 1. : 0.; }
@@ -32,7 +90,7 @@ ARB_D void pinv_small(const double* a, double* out) {
           be += U[i * N + q] * U[i * N + q];
           ga += U[i * N + p] * U[i * N + q];
         }
-        if (ga != 0. && fabs(ga) > 1e-17 * sqrt(al * be)) {
+        if (ga != 0. && fabs(ga) > 4e-16 * sqrt(al * be)) {   // columns orthogonal to working precision
           rotated = true;
           double zeta = (be - al) / (2. * ga);
           double t = copysign(1., zeta) / (fabs(zeta) + sqrt(1. + zeta * zeta));
@@ -306,21 +364,25 @@ ARB_HD double poly_val(const double* c, double x) {
   for (int k = D - 1; k >= 0; --k) f = f * x + c[k];
   return f;
 }
-// root of c in (lo, hi) given f(lo) = flo != 0 and a sign change on the bracket
+// root of c in (lo, hi) given f(lo) = flo != 0 and a sign change on the bracket.
+// Safeguarded Newton; stops when |f| is below its own rounding noise (running Horner bound)
+// or the step is below one ulp -- the older "|dx| <= 4e-16 |x|" test alone let Newton
+// wander inside the noise floor for the whole iteration budget.
 template <int D>
 ARB_HD double poly_refine(const double* c, double lo, double hi, double flo) {
   double x = 0.5 * (lo + hi);
   const bool lo_neg = flo < 0.;
-  for (int it = 0; it < 200; ++it) {
-    double f = c[D], df = 0.;
+  for (int it = 0; it < 64; ++it) {
+    double f = c[D], df = 0., e = fabs(c[D]);
+    const double ax = fabs(x);
 #pragma unroll
-    for (int k = D - 1; k >= 0; --k) { df = df * x + f; f = f * x + c[k]; }
-    if (f == 0.) break;
+    for (int k = D - 1; k >= 0; --k) { df = df * x + f; f = f * x + c[k]; e = e * ax + fabs(f); }
+    if (fabs(f) <= 2.5e-16 * e) break;
     if ((f < 0.) == lo_neg) lo = x; else hi = x;
     double xn = x - f / df;
     if (!(xn > lo && xn < hi)) xn = 0.5 * (lo + hi);
     if (xn == x || !(hi - lo > 0.)) break;
-    const bool done = fabs(xn - x) <= 4e-16 * fabs(xn);
+    const bool done = fabs(xn - x) <= 2.5e-16 * fabs(xn);
     x = xn;
     if (done) break;
   }
@@ -359,6 +421,70 @@ struct PolyRoots<1> {
     return 0;
   }
 };
+
+// Largest real root of the MONIC sextic p when it can be certified cheaply.
+//  - start at the Laguerre-Samuelson bound  mean + sqrt(5) * std  of the roots (an upper bound
+//    of every root when all six are real -- the case met in practice: the sliding matrices of
+//    constraints.py:815-821 had all-real spectra in every sampled contact problem);
+//  - Laguerre's iteration from the right of the largest root of a real-rooted polynomial
+//    decreases monotonically onto it with cubic convergence (4-6 iterations, no bracketing,
+//    the same trip count on every lane);
+//  - certificate, valid whatever the roots are: if all Taylor coefficients of p at x* are
+//    positive, p > 0 on (x*, inf), so x* is the largest real root.
+// Returns 1 (root in *root), or 0 when the fast path does not apply (complex roots near the
+// path, a multiple root, slow convergence): the caller then isolates the roots rigorously.
+#ifdef ARB_HOSTTEST_COUNTERS
+static long arb_fastroot_hits = 0;   // host unit tests only: how often the fast path certified its root
+#endif
+ARB_HD int poly6_largest_root_fast(const double* p, double* root) {
+  const double mean = -p[5] * (1. / 6.);
+  const double var = (p[5] * p[5] - 2. * p[4]) * (1. / 6.) - mean * mean;
+  if (!(var >= 0.)) return 0;
+  double x = mean + 2.2360679774997898 * sqrt(var);
+  x += 1e-12 * fabs(x) + 1e-300;
+  bool conv = false;
+  for (int it = 0; it < 12; ++it) {
+    // p, p', p''/2 by one Horner pass, with the running rounding bound of p
+    double f = 1., d1 = 0., d2 = 0., e = 1.;
+    const double ax = fabs(x);
+#pragma unroll
+    for (int k = 5; k >= 0; --k) {
+      d2 = d2 * x + d1;
+      d1 = d1 * x + f;
+      f = f * x + p[k];
+      e = e * ax + fabs(f);
+    }
+    if (fabs(f) <= 2.5e-16 * e) { conv = true; break; }
+    if (!(f > 0.)) return 0;                    // fell to the left of a root: not real-rooted
+    const double G = d1 / f;
+    const double H = G * G - 2. * d2 / f;
+    const double disc = 5. * (6. * H - G * G);
+    if (!(disc >= 0.) || !(G > 0.)) return 0;
+    const double a = 6. / (G + sqrt(disc));
+    const double xn = x - a;
+    if (!(a > 2.5e-16 * fabs(x))) { conv = true; break; }
+    x = xn;
+  }
+  if (!conv) return 0;
+  // Taylor coefficients of p at x (repeated synthetic division), b[1..5] must be > 0
+  double b[7];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) b[k] = p[k];
+  b[6] = 1.;
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+#pragma unroll
+    for (int k = 5; k >= j; --k) b[k] += x * b[k + 1];
+  bool pos = true;
+#pragma unroll
+  for (int k = 1; k < 6; ++k) pos = pos && (b[k] > 0.);
+  if (!pos) return 0;
+  *root = x;
+#ifdef ARB_HOSTTEST_COUNTERS
+  ++arb_fastroot_hits;
+#endif
+  return 1;
+}
 
 // A: 4x4 contact admittance block, alpha: the vector of constraints.py:807-808, mu: friction.
 // Returns false if the structured path does not apply (caller falls back to the general
@@ -432,10 +558,15 @@ ARB_HD bool sliding_root_structured(const double* A, const double* alpha, double
   for (int k = 0; k < 6; ++k) T = fmax(T, fabs(p[k]));
   T += 1.;
   if (!(T < 1e300)) return false;
-  double roots[6];
-  const int nr = PolyRoots<6>::run(p, T, roots);
-  if (nr == 0) { *found = false; *s_out = 0.; return true; }
-  double t = roots[nr - 1];
+  double t;
+  if (poly6_largest_root_fast(p, &t)) {
+    if (t < 0.) { *found = false; *s_out = 0.; return true; }   // every real eigenvalue is > 0
+  } else {
+    double roots[6];
+    const int nr = PolyRoots<6>::run(p, T, roots);
+    if (nr == 0) { *found = false; *s_out = 0.; return true; }
+    t = roots[nr - 1];
+  }
   // polish on det M(t):  f' = tr(adj(M) (2 t I + C1))
   for (int it = 0; it < 3; ++it) {
     double M[9], dM[9];

@@ -36,8 +36,12 @@ WORKLOADS = {
     "human36_free_4096": ("human36_free", 4096),
     "human36_contact_16384": ("human36_contact", 16384),
 }
-RESET_EVERY = 250   # steps after which worlds are re-initialised (the uncontrolled humanoid
-                    # collapses and the reference's own sliding solve diverges after ~0.35 s)
+EPISODE = 250      # steps after which a world is re-initialised (the uncontrolled humanoid
+                   # collapses and the reference's own sliding solve diverges after ~0.35 s)
+GROUPS = 10        # the batch is split into GROUPS contiguous blocks whose episodes are staggered
+PHASE = EPISODE//GROUPS   # by PHASE steps, so that at ANY step the batch holds every age of the
+                   # episode (free fall, first contacts, 8 contacts with ~20 % sliding) in equal
+                   # shares: the measured rate does not depend on which steps are timed
 
 
 def parse():
@@ -50,7 +54,7 @@ def parse():
     ap.add_argument("--worlds", type=int, default=0, help="override the total number of worlds")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=12.)
+    ap.add_argument("--cpu-seconds", type=float, default=20.)
     return ap.parse_args()
 
 
@@ -58,7 +62,7 @@ def parse():
 # CPU baseline: the oracle port of the reference on the host cores (multiprocessing)
 # ---------------------------------------------------------------------------------------
 def _cpu_worker(args):
-    scen, wid, seconds, warm = args
+    scen, wid, seconds = args
     for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[v] = "1"
     from arboris_b200 import scenarios
@@ -67,11 +71,12 @@ def _cpu_worker(args):
     model = flatten(scenarios.BUILDERS[scen]())
     o = OracleWorld(model.to_dict())
     o.gpos[:], o.gvel[:] = scenarios.initial_state(model, scen, wid)
-    # warm up past the free-fall so contacts are active like in the GPU run
-    for _ in range(warm):
-        o.step(DT)
+    o.step(DT)                                   # warm-up (imports, caches)
+    o.gpos[:], o.gvel[:] = scenarios.initial_state(model, scen, wid)
+    o.cforce[:] = 0.
+    # one whole episode from the reset state = the age mix the GPU batch holds at any step
     n, t0 = 0, time.perf_counter()
-    while time.perf_counter() - t0 < seconds and n < RESET_EVERY - warm:
+    while n < EPISODE and time.perf_counter() - t0 < seconds:
         o.step(DT)
         n += 1
     return n, time.perf_counter() - t0
@@ -83,15 +88,15 @@ def cpu_baseline(scen, seconds):
     for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[v] = "1"
     ctx = mp.get_context("spawn")
-    warm = 60 if scen == "human36_contact" else 5
     with ctx.Pool(cores) as pool:
-        res = pool.map(_cpu_worker, [(scen, w, seconds, warm) for w in range(cores)])
+        res = pool.map(_cpu_worker, [(scen, w, seconds) for w in range(cores)])
     steps = sum(r[0] for r in res)
     wall = max(r[1] for r in res)
+    nmin = min(r[0] for r in res)
     return {"value": steps/wall, "unit": "world-steps/s", "cores": cores, "kind": "port",
-            "sample": "%d worlds (one per core) x ~%d steps of %s after %d warm-up steps, "
-                      "numpy oracle port of the reference, BLAS threads = 1"
-                      % (cores, steps//max(cores, 1), scen, warm),
+            "sample": "%d worlds (one per core), each one episode of %s from its reset state "
+                      "(%d of %d steps done within the %.0f s cap), numpy oracle port of the "
+                      "reference, BLAS threads = 1" % (cores, scen, nmin, EPISODE, seconds),
             "per_core": steps/wall/cores}
 
 
@@ -133,24 +138,61 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons)}
 
 
+class Episodes(object):
+    """Staggered episodes over GROUPS contiguous blocks of the batch (see EPISODE).
+    ``state`` is a triple of (elem, W) tensors (device tensors of the BatchedWorld, or
+    pinned host tensors for the end-to-end pass), ``init`` the matching reset values."""
+
+    def __init__(self, W, state, init, step_fn):
+        from arboris_b200.shard import shard_range
+        self.blocks = [shard_range(W, g, GROUPS) for g in range(GROUPS)]
+        self.state, self.init, self.step_fn = state, init, step_fn
+        self.t = -(EPISODE - PHASE)
+        for g in range(GROUPS):
+            self.reset(g)
+
+    def reset(self, g):
+        w0, w1 = self.blocks[g]
+        if w1 > w0:
+            for dst, src in zip(self.state, self.init):
+                if src is None:
+                    dst[:, w0:w1].zero_()
+                else:
+                    dst[:, w0:w1].copy_(src[:, w0:w1])
+
+    def advance(self, k):
+        while k > 0:
+            if self.t % PHASE == 0:
+                for g in range(GROUPS):
+                    if (self.t + PHASE*g) % EPISODE == 0:
+                        self.reset(g)
+            c = min(k, PHASE - self.t % PHASE)
+            self.step_fn(c)
+            self.t += c
+            k -= c
+
+    def prime(self):
+        """Untimed: bring group g to age PHASE*g."""
+        self.advance(-self.t)
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
     from arboris_b200 import scenarios, _capi
     from arboris_b200.batch import BatchedWorld
     from arboris_b200.flatten import flatten
+    from arboris_b200.shard import env_rank, shard_range, reduce_report
 
-    world_size = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    rank, world_size, local = env_rank()
     torch.cuda.set_device(local)
     if world_size > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     scen, total = WORKLOADS[a.workload]
     if a.worlds:
         total = a.worlds
-    W = total // world_size                     # contiguous block of worlds per GPU
-    w0 = rank*W
+    w0, w1 = shard_range(total, rank, world_size)   # contiguous block of worlds per GPU
+    W = w1 - w0
     model = flatten(scenarios.BUILDERS[scen]())
     # synthetic seeded initial states; 4096 distinct worlds tiled over the shard
     nseed = min(W, 4096)
@@ -161,22 +203,8 @@ def run_ours(a):
     bw = BatchedWorld(model, W, device="cuda:%d" % local)
     gpos0 = torch.as_tensor(gp, device=bw.device)
     gvel0 = torch.as_tensor(gv, device=bw.device)
-
-    def reset():
-        bw.gpos.copy_(gpos0)
-        bw.gvel.copy_(gvel0)
-        bw.cforce.zero_()
-
-    def run_steps(k, done):
-        # k steps; worlds are re-initialised every RESET_EVERY steps (a device copy)
-        while k > 0:
-            if done % RESET_EVERY == 0:
-                reset()
-            c = min(k, RESET_EVERY - done % RESET_EVERY)
-            bw.step(DT, c)
-            k -= c
-            done += c
-        return done
+    ep = Episodes(W, (bw.gpos, bw.gvel, bw.cforce), (gpos0, gvel0, None),
+                  lambda c: bw.step(DT, c))
 
     def barrier():
         torch.cuda.synchronize()
@@ -184,57 +212,65 @@ def run_ours(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    ep.prime()                      # untimed: stagger the episodes
     warm = max(a.warmup, 3)
-    done = run_steps(warm, 0)
+    ep.advance(warm)
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
     l0 = bw.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    done = run_steps(a.steps, done)
+    ep.advance(a.steps)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
     launches = bw.launch_count() - l0
     sampler.stop_flag = True
-    status = bw.status()
-    nbad = int((status & 1).ne(0).sum())
-    g, v, _ = bw.gpos, bw.gvel, None
-    nonfinite = int((~torch.isfinite(v)).any(0).sum())
+    nonfinite = int((~torch.isfinite(bw.gvel)).any(0).sum())
+
+    # ---- per-stage device time (diagnostic pass, CUDA events around every kernel) ----------
+    bw.set_option("time_stages", 1)
+    ep.advance(PHASE)
+    torch.cuda.synchronize()
+    st = bw.stage_ms()
+    bw.set_option("time_stages", 0)
 
     # ---- end to end through the host-buffer entry point (arb_step_host) --------------------
     e2e = None
     if not a.no_e2e:
+        nrows = max(int(model.nrows), 1)
         hg = torch.empty(gp.shape, dtype=torch.float64).pin_memory()
         hv = torch.empty(gv.shape, dtype=torch.float64).pin_memory()
-        hf = torch.zeros((max(int(model.nrows), 1), W), dtype=torch.float64).pin_memory()
-        hg.copy_(torch.as_tensor(gp)); hv.copy_(torch.as_tensor(gv))
+        hf = torch.zeros((nrows, W), dtype=torch.float64).pin_memory()
+        hg.copy_(bw.gpos); hv.copy_(bw.gvel); hf.copy_(bw.cforce)    # continue the same episodes
         hgn, hvn, hfn = hg.numpy(), hv.numpy(), hf.numpy()
-        k_e2e = max(3, min(a.steps, 20))
-        for _ in range(3):
-            bw.step_host(hgn, hvn, hfn, DT, 1)
+        hep = Episodes.__new__(Episodes)
+        hep.blocks, hep.t = ep.blocks, ep.t
+        hep.state, hep.init = (hg, hv, hf), (torch.as_tensor(gp), torch.as_tensor(gv), None)
+
+        def host_steps(c):
+            for _ in range(c):
+                bw.step_host(hgn, hvn, hfn, DT, 1)    # H2D state, 1 step, D2H state, sync
+        hep.step_fn = host_steps
+        k_e2e = max(3, min(a.steps, 50))
+        hep.advance(3)
         barrier()
         t0 = time.perf_counter()
-        for _ in range(k_e2e):
-            bw.step_host(hgn, hvn, hfn, DT, 1)    # H2D state, 1 step, D2H state, sync
+        hep.advance(k_e2e)
         torch.cuda.synchronize()
         t_e2e = time.perf_counter() - t0
         bytes_in = (hgn.nbytes + hvn.nbytes + (hfn.nbytes if model.nrows else 0))
         e2e = [t_e2e/k_e2e, bytes_in, bytes_in, k_e2e]
 
     # max over ranks of the timed region; totals over ranks
-    t = torch.tensor([ms, e2e[0]*1e3 if e2e else 0.], device=bw.device, dtype=torch.float64)
-    cnt = torch.tensor([float(nonfinite), float(launches)], device=bw.device, dtype=torch.float64)
-    if world_size > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_all, e2e_ms = float(t[0]), float(t[1])
+    (ms_all, e2e_ms), (nonfinite, launches, total_worlds) = reduce_report(
+        [ms, e2e[0]*1e3 if e2e else 0.], [nonfinite, launches, W], device=bw.device)
     if rank != 0:
         if world_size > 1:
             dist.destroy_process_group()
         return
-    total_worlds = W*world_size
+    total_worlds = int(total_worlds)
     value = total_worlds*a.steps/(ms_all*1e-3)
     lib = _capi.load()
     peak = C_double()
@@ -242,12 +278,21 @@ def run_ours(a):
     fp64_peak = peak.value
     flop = FLOP_PER_WORLD_STEP[scen]
     achieved = (value/world_size)*flop        # per GPU, flop/s
-    peaks = {}
+    peaks, traffic = {}, {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(scen, {})
+    except Exception:
+        pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.))
+    nst = max(st["steps"], 1)
+    stage = {k: st[k]/nst for k in ("prepare", "gs", "finish")}
+    tot_stage = sum(stage.values()) or 1.
+    dom = max(stage, key=stage.get)
+    dram_per_world = traffic.get("dram_bytes_per_world_step")
     out = {
         "metric": "world-steps/s (human36, fp64, dt=1ms)", "value": value, "unit": "world-steps/s",
         "n_gpus": world_size, "steps": a.steps, "warmup": warm, "ms_per_step": ms_all/a.steps,
@@ -255,28 +300,39 @@ def run_ours(a):
         "data": "synthetic (seeded random initial states, SURVEY.md 8(d))",
         "config": {"workload": a.workload, "scenario": scen, "worlds_total": total_worlds,
                    "worlds_per_gpu": W, "dt": DT, "constraints": int(model.nc),
-                   "reset_every_steps": RESET_EVERY,
+                   "episode_steps": EPISODE, "episode_groups": GROUPS,
+                   "episodes": "worlds restart from their seeded state every %d steps; %d blocks of "
+                               "the batch are staggered by %d steps so every timed step sees the "
+                               "whole episode's mix of contact states" % (EPISODE, GROUPS, PHASE),
                    "l2": "state of all worlds (%.0f MB) and per-world scratch exceed L2; no flush needed"
-                         % (total_worlds/world_size*STATE_BYTES_PER_WORLD_STEP/2/1e6),
+                         % (W*STATE_BYTES_PER_WORLD_STEP/2/1e6),
                    "parallelism": "worlds sharded over %d GPU(s), no collective on the step path" % world_size},
-        "gpu_launches": int(cnt[1]),
-        "nonfinite_worlds": int(cnt[0]),
+        "gpu_launches": int(launches),
+        "nonfinite_worlds": int(nonfinite),
         "roofline": {"bound": "fp64", "achieved": achieved/1e12, "peak": fp64_peak/1e12,
                      "unit": "TFLOP/s", "frac": achieved/fp64_peak if fp64_peak else None,
-                     "traffic": None,
+                     "traffic": dram_per_world*W if dram_per_world else None,
+                     "traffic_note": traffic.get("source"),
                      "peak_source": "DFMA micro-benchmark measured in this run (arb_measure_fp64_peak); "
                                     "MEASURED_PEAKS.json has no fp64 entry",
                      "flop_per_world_step": flop,
+                     "per_launch": "one (prepare, gs, finish) triple = one step of the %d worlds of a GPU; "
+                                   "achieved = worlds x flop_per_world_step / step time" % W,
+                     "stage_ms": stage, "dominant_kernel": "k_fused_" + dom,
+                     "dominant_share": stage[dom]/tot_stage,
                      "hbm": {"achieved": value/world_size*STATE_BYTES_PER_WORLD_STEP/1e9,
                              "peak": hbm_peak, "unit": "GB/s",
-                             "frac": value/world_size*STATE_BYTES_PER_WORLD_STEP/1e9/hbm_peak}},
+                             "frac": value/world_size*STATE_BYTES_PER_WORLD_STEP/1e9/hbm_peak,
+                             "dram_achieved": (dram_per_world*value/world_size/1e9
+                                               if dram_per_world else None)}},
         "clocks": sampler.summary(),
     }
     if e2e:
         out["e2e"] = {"value": total_worlds/(e2e_ms*1e-3), "unit": "world-steps/s",
                       "h2d_bytes_per_step": e2e[1]*world_size, "d2h_bytes_per_step": e2e[2]*world_size,
                       "steps": e2e[3], "how": "arb_step_host: pinned host state -> device, 1 step, "
-                                              "device -> host, synchronised, every step"}
+                                              "device -> host, synchronised, every step; same staggered "
+                                              "episodes as the timed region"}
     if not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(scen, a.cpu_seconds)
     print(json.dumps(out))

@@ -129,7 +129,9 @@ int arb_batch_create(const arb_model *model, int64_t nworlds, int device, void *
 void arb_batch_destroy(arb_batch *batch);
 int arb_batch_set_stream(arb_batch *batch, void *stream);
 /* tuning/testing switches: "force_phases" (1: arb_step runs the four API phase kernels
- * instead of the fused stages), "prepare_warp" (0: lane-per-world prepare stage) */
+ * instead of the fused stages), "time_stages" (1: CUDA events around every fused stage,
+ * synchronising after every step -- a diagnostic for bench.py, read with arb_batch_stage_ms;
+ * setting it clears the accumulators) */
 int arb_batch_set_option(arb_batch *batch, const char *name, int value);
 
 /* caller-owned DEVICE state, layouts in the header comment */
@@ -160,6 +162,9 @@ int arb_batch_status(arb_batch *batch, int32_t *flags);
 
 /* counters for bench.py: kernels launched by this library since batch creation */
 int64_t arb_batch_launch_count(const arb_batch *batch);
+/* accumulated device milliseconds of the fused stages since "time_stages" was set:
+ * out4 = {prepare, gs, finish, number of steps timed} */
+int arb_batch_stage_ms(const arb_batch *batch, double *out4);
 /* measured fp64 FMA throughput of the device in flop/s (DFMA micro-benchmark, about 50 ms) */
 int arb_measure_fp64_peak(int device, double *flops_per_s);
 

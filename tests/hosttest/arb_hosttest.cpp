@@ -3,6 +3,7 @@
 // `pytest -m "not gpu"` can check the arithmetic against the oracle without a
 // GPU.  Built by tests/hosttest/build.py into tests/hosttest/_build/; the
 // arboris_b200 package never loads it (the product path is CUDA only).
+#define ARB_HOSTTEST_COUNTERS 1
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -133,6 +134,7 @@ int ht_sliding_root(const double* A, const double* alpha, double mu, double* s, 
   *found = f ? 1 : 0;
   return ok ? 1 : 0;
 }
+long ht_fastroot_hits() { return arb_fastroot_hits; }
 int ht_solve4(const double* a, const double* b, double* x) { return solve_small<4>(a, b, x) ? 1 : 0; }
 void ht_exp(const double* tw, double* out12) {
   Se3 h;
