@@ -25,16 +25,20 @@
 // controllers.py:43-60), the constraint generators use unit wrenches on the bodies that
 // carry constraint frames, and the final velocity uses the Gauss-Seidel wrenches.
 //
-// One world per lane; every array is [elem][W] (coalesced over the lanes of a warp).
+// One world per lane; scratch arrays are tiled [W/32][elem][32] (each access of a warp is one
+// 256-byte segment).
 #pragma once
 #include "arb_constraints.cuh"
 #include "arb_joints.cuh"
 #include "arb_math.cuh"
 #include "arb_types.h"
 
-#ifndef AT
-#define AT(ptr, idx) (ptr)[(int64_t)(idx) * W + w]
-#endif
+// Addressing.  FT = fused scratch: tile layout [W/32][elem][32] reached through per-thread
+// pre-offset pointers (fused_tile_view, arb_fused.cuh), so an element index costs no 64-bit
+// arithmetic -- with a compile-time index the load is one LDG with an immediate offset.
+// ST = caller-owned state arrays, [elem][W] (the ABI layout of include/arboris_b200.h).
+#define FT(ptr, idx) (ptr)[(idx) * ARB_TILE]
+#define ST(ptr, idx) (ptr)[(int64_t)(idx) * b.W + w]
 
 // y = X^T x for a wrench x = [m; f], X = Ad(H^-1):  [R m + p x (R f) ; R f]
 ARB_HD void wrench_up(const Se3& h, const double* x, double* y) {
@@ -74,31 +78,30 @@ ARB_HD void adj_apply(const double* t, const double* x, double* y) {
   y[3] = b2[0] + c[0]; y[4] = b2[1] + c[1]; y[5] = b2[2] + c[2];
 }
 
-ARB_D void load_se3(const double* arr, int j, int64_t W, int64_t w, Se3& h) {
+ARB_D void load_se3(const double* arr, int j, Se3& h) {
 #pragma unroll
-  for (int i = 0; i < 9; ++i) h.R[i] = AT(arr, j * 12 + i);
+  for (int i = 0; i < 9; ++i) h.R[i] = FT(arr, j * 12 + i);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) h.p[i] = AT(arr, j * 12 + 9 + i);
+  for (int i = 0; i < 3; ++i) h.p[i] = FT(arr, j * 12 + 9 + i);
 }
-ARB_D void store_se3(double* arr, int j, int64_t W, int64_t w, const Se3& h) {
+ARB_D void store_se3(double* arr, int j, const Se3& h) {
 #pragma unroll
-  for (int i = 0; i < 9; ++i) AT(arr, j * 12 + i) = h.R[i];
+  for (int i = 0; i < 9; ++i) FT(arr, j * 12 + i) = h.R[i];
 #pragma unroll
-  for (int i = 0; i < 3; ++i) AT(arr, j * 12 + 9 + i) = h.p[i];
+  for (int i = 0; i < 3; ++i) FT(arr, j * 12 + 9 + i) = h.p[i];
 }
 
 // ---------------------------------------------------------------------------------------
 // root-to-leaf pass: body poses and twists (core.py:1295-1308), theta, X, s, s^
 ARB_D void artic_kinematics(const DevModel& m, const DevBatch& b, int64_t w) {
-  const int64_t W = b.W;
   for (int j = 0; j < m.nj; ++j) {
     const int type = m.jtype[j];
     const int par = m.jparent[j];
     const int nd = arb_joint_ndof(type);
     const int dof = m.jdof[j];
     double q[16], dq[6];
-    for (int i = 0; i < arb_joint_ngpos(type); ++i) q[i] = AT(b.gpos, m.jgpos[j] + i);
-    for (int i = 0; i < nd; ++i) dq[i] = AT(b.gvel, dof + i);
+    for (int i = 0; i < arb_joint_ngpos(type); ++i) q[i] = ST(b.gpos, m.jgpos[j] + i);
+    for (int i = 0; i < nd; ++i) dq[i] = ST(b.gvel, dof + i);
     JointKin k;
     joint_kinematics(type, q, dq, k);
     const bool ident = m.hcn_ident[j] != 0;
@@ -121,13 +124,13 @@ ARB_D void artic_kinematics(const DevModel& m, const DevBatch& b, int64_t w) {
       for (int i = 0; i < 6; ++i) { Tp[i] = 0.; thp[i] = 0.; }
     } else {
       Se3 Hgp;
-      load_se3(b.fpose, par - 1, W, w, Hgp);
+      load_se3(b.fpose, par - 1, Hgp);
       se3_mul(Hgp, Hpc, Hgc);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { Tp[i] = AT(b.atw, (par - 1) * 6 + i); thp[i] = AT(b.ath, (par - 1) * 6 + i); }
+      for (int i = 0; i < 6; ++i) { Tp[i] = FT(b.atw, (par - 1) * 6 + i); thp[i] = FT(b.ath, (par - 1) * 6 + i); }
     }
-    store_se3(b.fpose, j, W, w, Hgc);
-    store_se3(b.aX, j, W, w, Hpc);
+    store_se3(b.fpose, j, Hgc);
+    store_se3(b.aX, j, Hpc);
     // child twist = Ad_cp T_p + Ad_cn T_nr                               (core.py:1308)
     double ta[6], tb[6], th[6];
     iad_apply(Hpc, Tp, ta);
@@ -138,7 +141,7 @@ ARB_D void artic_kinematics(const DevModel& m, const DevBatch& b, int64_t w) {
       ad_apply(Hcn, k.T, tb);
     }
 #pragma unroll
-    for (int i = 0; i < 6; ++i) AT(b.atw, j * 6 + i) = ta[i] + tb[i];
+    for (int i = 0; i < 6; ++i) FT(b.atw, j * 6 + i) = ta[i] + tb[i];
     // theta_c = X_c theta_p - Ad_cn Ad_nr Ad_nr T_nr
     {
       Se3 Hnr;
@@ -154,7 +157,7 @@ ARB_D void artic_kinematics(const DevModel& m, const DevBatch& b, int64_t w) {
       }
       iad_apply(Hpc, thp, ta);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { th[i] = ta[i] - tau[i]; AT(b.ath, j * 6 + i) = th[i]; }
+      for (int i = 0; i < 6; ++i) { th[i] = ta[i] - tau[i]; FT(b.ath, j * 6 + i) = th[i]; }
     }
     // own columns: s = Ad_cn S, s^ = Ad_cn dS - adjacency(theta) s         (core.py:1310,1313)
     for (int c = 0; c < nd; ++c) {
@@ -176,8 +179,8 @@ ARB_D void artic_kinematics(const DevModel& m, const DevBatch& b, int64_t w) {
       adj_apply(th, s, as);
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        AT(b.aS, (dof + c) * 6 + i) = s[i];
-        AT(b.aSh, (dof + c) * 6 + i) = ds[i] - as[i];
+        FT(b.aS, (dof + c) * 6 + i) = s[i];
+        FT(b.aSh, (dof + c) * 6 + i) = ds[i] - as[i];
       }
     }
   }
@@ -185,16 +188,14 @@ ARB_D void artic_kinematics(const DevModel& m, const DevBatch& b, int64_t w) {
 
 // generalized force of the (diagonal) PD controllers on dof k        (controllers.py:141-159)
 ARB_D double artic_tau(const DevModel& m, const DevBatch& b, int64_t w, int k) {
-  const int64_t W = b.W;
   if (!m.has_pd || m.pd_gpos[k] < 0) return 0.;
-  return m.pd_kp[k] * (m.pd_qd[k] - AT(b.gpos, m.pd_gpos[k])) + m.pd_c[k];
+  return m.pd_kp[k] * (m.pd_qd[k] - ST(b.gpos, m.pd_gpos[k])) + m.pd_c[k];
 }
 
 // ---------------------------------------------------------------------------------------
 // leaf-to-root pass: elimination of every dof (stores U, LA, LM, 1/d) together with the
 // reduced right-hand side u of the free motion (w_b = M_b (T_b/dt + gravity_b), tau = PD).
 ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double dt) {
-  const int64_t W = b.W;
   bool ok = true;
   const double gt[6] = {0., 0., 0., m.gravity * m.up[0], m.gravity * m.up[1], m.gravity * m.up[2]};
   for (int j = m.nj - 1; j >= 0; --j) {
@@ -207,7 +208,7 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
     double IA[36], IM[36], beta[6];
     double T[6], th[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { T[i] = AT(b.atw, j * 6 + i); th[i] = AT(b.ath, j * 6 + i); }
+    for (int i = 0; i < 6; ++i) { T[i] = FT(b.atw, j * 6 + i); th[i] = FT(b.ath, j * 6 + i); }
     if (flags & ARB_BODY_HASMASS) {
       // A_b = M_b/dt + B_b + Omega(T) M_b + M_b adjacency(theta)
       double X3[9];
@@ -248,7 +249,7 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
       for (int i = 0; i < 6; ++i) a[i] = T[i] / dt;
       if ((flags & ARB_BODY_MASSIVE) && m.nweight > 0) {
         Se3 H;
-        load_se3(b.fpose, j, W, w, H);
+        load_se3(b.fpose, j, H);
         double g[6];
         iad_apply(H, gt, g);
 #pragma unroll
@@ -274,15 +275,15 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
     }
     if (m.jhaschild[j]) {
 #pragma unroll
-      for (int i = 0; i < 36; ++i) { IA[i] += AT(b.aIA, j * 36 + i); IM[i] += AT(b.aIM, j * 36 + i); }
+      for (int i = 0; i < 36; ++i) { IA[i] += FT(b.aIA, j * 36 + i); IM[i] += FT(b.aIM, j * 36 + i); }
 #pragma unroll
-      for (int i = 0; i < 6; ++i) beta[i] += AT(b.abeta, j * 6 + i);
+      for (int i = 0; i < 6; ++i) beta[i] += FT(b.abeta, j * 6 + i);
     }
     for (int c = nd - 1; c >= 0; --c) {
       const int k = dof + c;
       double s[6], sh[6], U[6], LA[6], LM[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { s[i] = AT(b.aS, k * 6 + i); sh[i] = AT(b.aSh, k * 6 + i); }
+      for (int i = 0; i < 6; ++i) { s[i] = FT(b.aS, k * 6 + i); sh[i] = FT(b.aSh, k * 6 + i); }
       double d = 0., sb = 0.;
 #pragma unroll
       for (int r = 0; r < 6; ++r) {
@@ -305,10 +306,10 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
         LM[i] = tm * dinv;
       }
       const double u = (artic_tau(m, b, w, k) - sb) * dinv;
-      AT(b.au, k) = u;
-      AT(b.adinv, k) = dinv;
+      FT(b.au, k) = u;
+      FT(b.adinv, k) = dinv;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { AT(b.aU, k * 6 + i) = U[i]; AT(b.aLA, k * 6 + i) = LA[i]; AT(b.aLM, k * 6 + i) = LM[i]; }
+      for (int i = 0; i < 6; ++i) { FT(b.aU, k * 6 + i) = U[i]; FT(b.aLA, k * 6 + i) = LA[i]; FT(b.aLM, k * 6 + i) = LM[i]; }
       if (c > 0 || par != 0) {
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
@@ -320,7 +321,7 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
     }
     if (par != 0) {
       Se3 X;
-      load_se3(b.aX, j, W, w, X);
+      load_se3(b.aX, j, X);
       congruence_up(X, IA);
       congruence_up(X, IM);
       double bu[6];
@@ -328,14 +329,14 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
       const int pj = par - 1;
       if (m.jaccfirst[j]) {
 #pragma unroll
-        for (int i = 0; i < 36; ++i) { AT(b.aIA, pj * 36 + i) = IA[i]; AT(b.aIM, pj * 36 + i) = IM[i]; }
+        for (int i = 0; i < 36; ++i) { FT(b.aIA, pj * 36 + i) = IA[i]; FT(b.aIM, pj * 36 + i) = IM[i]; }
 #pragma unroll
-        for (int i = 0; i < 6; ++i) AT(b.abeta, pj * 6 + i) = bu[i];
+        for (int i = 0; i < 6; ++i) FT(b.abeta, pj * 6 + i) = bu[i];
       } else {
 #pragma unroll
-        for (int i = 0; i < 36; ++i) { AT(b.aIA, pj * 36 + i) += IA[i]; AT(b.aIM, pj * 36 + i) += IM[i]; }
+        for (int i = 0; i < 36; ++i) { FT(b.aIA, pj * 36 + i) += IA[i]; FT(b.aIM, pj * 36 + i) += IM[i]; }
 #pragma unroll
-        for (int i = 0; i < 6; ++i) AT(b.abeta, pj * 6 + i) += bu[i];
+        for (int i = 0; i < 6; ++i) FT(b.abeta, pj * 6 + i) += bu[i];
       }
     }
   }
@@ -348,7 +349,6 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
 // to `x`; (V, Vh) of every body with children is kept in aV[j][0..11].
 template <bool MARKED_U>
 ARB_D void artic_forward_full(const DevModel& m, const DevBatch& b, int64_t w, const double* u, double* x) {
-  const int64_t W = b.W;
   for (int j = 0; j < m.nj; ++j) {
     const int par = m.jparent[j];
     const int nd = arb_joint_ndof(m.jtype[j]);
@@ -359,28 +359,28 @@ ARB_D void artic_forward_full(const DevModel& m, const DevBatch& b, int64_t w, c
       for (int i = 0; i < 6; ++i) { V[i] = 0.; Vh[i] = 0.; }
     } else {
       Se3 X;
-      load_se3(b.aX, j, W, w, X);
+      load_se3(b.aX, j, X);
       double vp[6], vhp[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { vp[i] = AT(b.aV, (par - 1) * 72 + i); vhp[i] = AT(b.aV, (par - 1) * 72 + 6 + i); }
+      for (int i = 0; i < 6; ++i) { vp[i] = FT(b.aV, (par - 1) * 72 + i); vhp[i] = FT(b.aV, (par - 1) * 72 + 6 + i); }
       iad_apply(X, vp, V);
       iad_apply(X, vhp, Vh);
     }
     const bool useu = !MARKED_U || m.jmark[j];
     for (int c = 0; c < nd; ++c) {
       const int k = dof + c;
-      double t = useu ? AT(u, k) : 0.;
+      double t = useu ? FT(u, k) : 0.;
       if (par != 0 || c > 0) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) t -= AT(b.aLA, k * 6 + i) * V[i] + AT(b.aLM, k * 6 + i) * Vh[i];
+        for (int i = 0; i < 6; ++i) t -= FT(b.aLA, k * 6 + i) * V[i] + FT(b.aLM, k * 6 + i) * Vh[i];
       }
-      AT(x, k) = t;
+      FT(x, k) = t;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { V[i] += AT(b.aS, k * 6 + i) * t; Vh[i] += AT(b.aSh, k * 6 + i) * t; }
+      for (int i = 0; i < 6; ++i) { V[i] += FT(b.aS, k * 6 + i) * t; Vh[i] += FT(b.aSh, k * 6 + i) * t; }
     }
     if (m.jhaschild[j] || m.jmark[j]) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { AT(b.aV, j * 72 + i) = V[i]; AT(b.aV, j * 72 + 6 + i) = Vh[i]; }
+      for (int i = 0; i < 6; ++i) { FT(b.aV, j * 72 + i) = V[i]; FT(b.aV, j * 72 + 6 + i) = Vh[i]; }
     }
   }
 }
@@ -392,7 +392,6 @@ ARB_D void artic_forward_full(const DevModel& m, const DevBatch& b, int64_t w, c
 //  marked joints.  (V of each marked body is left in aV[j][r*12 ..], x in ax[r][k].)
 template <int NR>
 ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t w, int body, int kstart) {
-  const int64_t W = b.W;
   const int n = m.ndof;
   const int off = m.coloff[body];
   double beta[NR][6];
@@ -406,8 +405,8 @@ ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t 
     const int j = m.dofjoint[k];
     double s[6], U[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { s[i] = AT(b.aS, k * 6 + i); U[i] = AT(b.aU, k * 6 + i); }
-    const double dinv = AT(b.adinv, k);
+    for (int i = 0; i < 6; ++i) { s[i] = FT(b.aS, k * 6 + i); U[i] = FT(b.aU, k * 6 + i); }
+    const double dinv = FT(b.adinv, k);
     const bool last = (l == 0);
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
@@ -416,7 +415,7 @@ ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t 
       for (int i = 0; i < 6; ++i) sb += s[i] * beta[r][i];
       const double tau = (k == kstart) ? 1. : 0.;
       const double u = (tau - sb) * dinv;
-      AT(b.au, r * n + k) = u;
+      FT(b.au, r * n + k) = u;
       if (!last) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) beta[r][i] += U[i] * u;
@@ -424,7 +423,7 @@ ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t 
     }
     if (k == m.jdof[j] && m.jparent[j] != 0) {
       Se3 X;
-      load_se3(b.aX, j, W, w, X);
+      load_se3(b.aX, j, X);
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
         double y[6];
@@ -449,14 +448,14 @@ ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t 
         for (int i = 0; i < 6; ++i) { V[r][i] = 0.; Vh[r][i] = 0.; }
     } else {
       Se3 X;
-      load_se3(b.aX, j, W, w, X);
+      load_se3(b.aX, j, X);
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
         double vp[6], vhp[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          vp[i] = AT(b.aV, (par - 1) * 72 + r * 12 + i);
-          vhp[i] = AT(b.aV, (par - 1) * 72 + r * 12 + 6 + i);
+          vp[i] = FT(b.aV, (par - 1) * 72 + r * 12 + i);
+          vhp[i] = FT(b.aV, (par - 1) * 72 + r * 12 + 6 + i);
         }
         iad_apply(X, vp, V[r]);
         iad_apply(X, vhp, Vh[r]);
@@ -469,17 +468,17 @@ ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t 
       double LA[6], LM[6], s[6], sh[6];
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        LA[i] = AT(b.aLA, k * 6 + i); LM[i] = AT(b.aLM, k * 6 + i);
-        s[i] = AT(b.aS, k * 6 + i); sh[i] = AT(b.aSh, k * 6 + i);
+        LA[i] = FT(b.aLA, k * 6 + i); LM[i] = FT(b.aLM, k * 6 + i);
+        s[i] = FT(b.aS, k * 6 + i); sh[i] = FT(b.aSh, k * 6 + i);
       }
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
-        double t = onpath ? AT(b.au, r * n + k) : 0.;
+        double t = onpath ? FT(b.au, r * n + k) : 0.;
         if (par != 0 || c > 0) {
 #pragma unroll
           for (int i = 0; i < 6; ++i) t -= LA[i] * V[r][i] + LM[i] * Vh[r][i];
         }
-        AT(b.ax, r * n + k) = t;
+        FT(b.ax, r * n + k) = t;
 #pragma unroll
         for (int i = 0; i < 6; ++i) { V[r][i] += s[i] * t; Vh[r][i] += sh[i] * t; }
       }
@@ -488,8 +487,8 @@ ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t 
     for (int r = 0; r < NR; ++r)
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        AT(b.aV, j * 72 + r * 12 + i) = V[r][i];
-        AT(b.aV, j * 72 + r * 12 + 6 + i) = Vh[r][i];
+        FT(b.aV, j * 72 + r * 12 + i) = V[r][i];
+        FT(b.aV, j * 72 + r * 12 + 6 + i) = Vh[r][i];
       }
   }
 }
@@ -497,16 +496,14 @@ ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t 
 // row `g` of the generator matrix G applied to the solution r of the last solve:
 // body generators read V of their body, joint-limit generators the dof itself.
 ARB_D double artic_gen_value(const DevModel& m, const DevBatch& b, int64_t w, int g, int r, const double* x) {
-  const int64_t W = b.W;
-  if (g < 6 * m.ngen) return AT(b.aV, (m.gen_body[g / 6] - 1) * 72 + r * 12 + g % 6);
-  return AT(x, r * m.ndof + m.glimdof[g - 6 * m.ngen]);
+  if (g < 6 * m.ngen) return FT(b.aV, (m.gen_body[g / 6] - 1) * 72 + r * 12 + g % 6);
+  return FT(x, r * m.ndof + m.glimdof[g - 6 * m.ngen]);
 }
 
 // ---------------------------------------------------------------------------------------
 // leaf-to-root pass over the marked joints for the Gauss-Seidel result y (wrenches on the
 // generator bodies, generalized forces on the limited dofs): u -> au[0][k] (marked dofs).
 ARB_D void artic_backward_wrenches(const DevModel& m, const DevBatch& b, int64_t w, const double* y) {
-  const int64_t W = b.W;
   const int NG6 = 6 * m.ngen;
   for (int j = m.nj - 1; j >= 0; --j) {
     if (!m.jmark[j]) continue;
@@ -517,39 +514,39 @@ ARB_D void artic_backward_wrenches(const DevModel& m, const DevBatch& b, int64_t
     for (int g = 0; g < m.ngen; ++g)
       if (m.gen_body[g] == j + 1) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) beta[i] -= AT(y, 6 * g + i);
+        for (int i = 0; i < 6; ++i) beta[i] -= FT(y, 6 * g + i);
       }
     if (m.jmarkchild[j]) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) beta[i] += AT(b.abeta, j * 6 + i);
+      for (int i = 0; i < 6; ++i) beta[i] += FT(b.abeta, j * 6 + i);
     }
     for (int c = nd - 1; c >= 0; --c) {
       const int k = dof + c;
       double tau = 0.;
       for (int g = NG6; g < m.ngrows; ++g)
-        if (m.glimdof[g - NG6] == k) tau += AT(y, g);
+        if (m.glimdof[g - NG6] == k) tau += FT(y, g);
       double sb = 0.;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) sb += AT(b.aS, k * 6 + i) * beta[i];
-      const double u = (tau - sb) * AT(b.adinv, k);
-      AT(b.au, k) = u;
+      for (int i = 0; i < 6; ++i) sb += FT(b.aS, k * 6 + i) * beta[i];
+      const double u = (tau - sb) * FT(b.adinv, k);
+      FT(b.au, k) = u;
       if (c > 0 || par != 0) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) beta[i] += AT(b.aU, k * 6 + i) * u;
+        for (int i = 0; i < 6; ++i) beta[i] += FT(b.aU, k * 6 + i) * u;
       }
     }
     if (par != 0) {
       Se3 X;
-      load_se3(b.aX, j, W, w, X);
+      load_se3(b.aX, j, X);
       double bu[6];
       wrench_up(X, beta, bu);
       const int pj = par - 1;
       if (m.jmarkfirst[j]) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) AT(b.abeta, pj * 6 + i) = bu[i];
+        for (int i = 0; i < 6; ++i) FT(b.abeta, pj * 6 + i) = bu[i];
       } else {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) AT(b.abeta, pj * 6 + i) += bu[i];
+        for (int i = 0; i < 6; ++i) FT(b.abeta, pj * 6 + i) += bu[i];
       }
     }
   }

@@ -1,5 +1,6 @@
 // Fused step driver: prepare -> gs -> finish per time step (see arb_fused.cuh).
-// All three stages are lane-per-world (one world per thread, [elem][W] arrays).
+// All three stages are lane-per-world (one world per thread); the scratch between them is tiled
+// [W/32][elem][32] (arb_types.h).
 #include <cuda_runtime.h>
 #include <string>
 
@@ -25,15 +26,15 @@ struct FusedState {
 __global__ void __launch_bounds__(FUSED_THREADS) k_fused_prepare_lane(DevModel m, DevBatch b, double dt) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= b.W) return;
-  world_fused_prepare(m, b, w, dt);
+  world_fused_prepare(m, fused_tile_view(b, w), w, dt);
 }
 __global__ void __launch_bounds__(FUSED_THREADS) k_fused_gs(DevModel m, DevBatch b, double dt) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w < b.W) world_fused_gs(m, b, w, dt);
+  if (w < b.W) world_fused_gs(m, fused_tile_view(b, w), w, dt);
 }
 __global__ void __launch_bounds__(FUSED_THREADS) k_fused_finish(DevModel m, DevBatch b, double dt) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w < b.W) world_fused_finish(m, b, w, dt);
+  if (w < b.W) world_fused_finish(m, fused_tile_view(b, w), w, dt);
 }
 
 // the fused stages fold controllers per dof: PD gains must be diagonal (arb_model_host.h)
@@ -42,13 +43,13 @@ bool arb_fused_supported(const arb_batch* b) { return b->model->host.fused_ok !=
 static int ensure_fused_scratch(arb_batch* b) {
   if (b->fused) return 0;
   FusedSizes s = fused_sizes(b->model->host);
-  const int64_t W = b->d.W;
+  const int64_t W = fused_padded_worlds(b->d.W);
   FusedState* f = new FusedState();
   CUDA_OKF(cudaMalloc((void**)&f->dbl, sizeof(double) * s.total_doubles() * W));
   CUDA_OKF(cudaMalloc((void**)&f->ints, sizeof(int) * s.total_ints() * W));
   CUDA_OKF(cudaMemsetAsync(f->dbl, 0, sizeof(double) * s.total_doubles() * W, b->stream));
   CUDA_OKF(cudaMemsetAsync(f->ints, 0, sizeof(int) * s.total_ints() * W, b->stream));
-  carve_fused(s, W, f->dbl, f->ints, b->d);
+  carve_fused(s, f->dbl, f->ints, b->d);
   b->fused = f;
   return 0;
 }

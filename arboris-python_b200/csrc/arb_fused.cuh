@@ -19,6 +19,22 @@
 #include "arb_constraints.cuh"
 #include "arb_world.cuh"
 
+// Per-thread view of the fused scratch: every pointer moved to this world's slot of its tile
+// (see FT in arb_artic.cuh).  All double arrays share one record per tile of ARB_TILE worlds
+// (frec doubles per world), all int arrays another (firec), so one offset serves each kind.
+ARB_D DevBatch fused_tile_view(const DevBatch& b, int64_t w) {
+  DevBatch t = b;
+  const int64_t tile = w / ARB_TILE, lane = w % ARB_TILE;
+  const int64_t od = tile * b.frec * ARB_TILE + lane, oi = tile * b.firec * ARB_TILE + lane;
+  t.fq += od; t.fLam += od; t.fv0 += od; t.fT1 += od; t.fT0 += od; t.fu += od; t.fy += od;
+  t.fAcc += od; t.fP += od; t.faux += od; t.fpose += od; t.ff += od;
+  t.aX += od; t.atw += od; t.ath += od; t.aS += od; t.aSh += od; t.aU += od; t.aLA += od;
+  t.aLM += od; t.adinv += od; t.aIA += od; t.aIM += od; t.abeta += od; t.au += od; t.ax += od;
+  t.aV += od;
+  t.factive += oi; t.fbranch += oi;
+  return t;
+}
+
 // Per-constraint update from body poses/twists: activation, aux (sdist / pos0 / q) and the
 // maps T1 (from body1's twist) and T0 (from body0's twist) to the constraint rows.
 // Returns the active flag.  pose/twist accessors go through P (12 doubles) and TW (6).
@@ -98,7 +114,6 @@ ARB_D bool constraint_update(const DevModel& m, int c, const Se3& P0, const Se3&
 // ---------------------------------------------------------------------------------------
 // prepare: see the header.  Reads the bound state only; writes the fused scratch.
 ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, double dt) {
-  const int64_t W = b.W;
   const int NG = m.ngrows;
   artic_kinematics(m, b, w);
   if (!artic_factor(m, b, w, dt)) b.status[w] |= ARB_STATUS_SINGULAR;
@@ -109,8 +124,8 @@ ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, 
     const int* ci = m.cint + ARB_CONS_NINT * c;
     const int type = m.ctype[c];
     const int r0 = m.crow[c];
-    AT(b.factive, c) = 0;
-    AT(b.fbranch, c) = 0;
+    FT(b.factive, c) = 0;
+    FT(b.fbranch, c) = 0;
     if (!ci[3]) continue;
     double aux[4] = {0., 0., 0., 0.}, T1[24], T0[24];
     int zi[3] = {0, 0, 0};
@@ -118,139 +133,370 @@ ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, 
     if (type == ARB_CONS_JOINT_LIMITS) {
       Se3 I;
       se3_identity(I);
-      act = constraint_update(m, c, I, I, nullptr, nullptr, AT(b.gpos, ci[2]), dt, aux, T1, T0, zi);
-      AT(b.cforce, r0) = 0.;
+      act = constraint_update(m, c, I, I, nullptr, nullptr, ST(b.gpos, ci[2]), dt, aux, T1, T0, zi);
+      ST(b.cforce, r0) = 0.;
     } else {
       Se3 P0, P1;
       double TW0[6], TW1[6];
-      if (ci[0] == 0) se3_identity(P0); else load_se3(b.fpose, ci[0] - 1, W, w, P0);
-      if (ci[1] == 0) se3_identity(P1); else load_se3(b.fpose, ci[1] - 1, W, w, P1);
+      if (ci[0] == 0) se3_identity(P0); else load_se3(b.fpose, ci[0] - 1, P0);
+      if (ci[1] == 0) se3_identity(P1); else load_se3(b.fpose, ci[1] - 1, P1);
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
-        TW0[i] = (ci[0] == 0) ? 0. : AT(b.atw, (ci[0] - 1) * 6 + i);
-        TW1[i] = (ci[1] == 0) ? 0. : AT(b.atw, (ci[1] - 1) * 6 + i);
+        TW0[i] = (ci[0] == 0) ? 0. : FT(b.atw, (ci[0] - 1) * 6 + i);
+        TW1[i] = (ci[1] == 0) ? 0. : FT(b.atw, (ci[1] - 1) * 6 + i);
       }
       act = constraint_update(m, c, P0, P1, TW0, TW1, 0., dt, aux, T1, T0, zi);
       if (type == ARB_CONS_SOFT_FINGER_PLANE_POINT) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) AT(b.cforce, r0 + i) = 0.;
+        for (int i = 0; i < 4; ++i) ST(b.cforce, r0 + i) = 0.;
       }
       if (act) {
         const int nr = arb_cons_ndol(type);
-        for (int i = 0; i < nr * 6; ++i) { AT(b.fT1, c * 24 + i) = T1[i]; AT(b.fT0, c * 24 + i) = T0[i]; }
+        for (int i = 0; i < nr * 6; ++i) { FT(b.fT1, c * 24 + i) = T1[i]; FT(b.fT0, c * 24 + i) = T0[i]; }
       }
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) AT(b.faux, 4 * c + i) = aux[i];
-    AT(b.factive, c) = act ? 1 : 0;
+    for (int i = 0; i < 4; ++i) FT(b.faux, 4 * c + i) = aux[i];
+    FT(b.factive, c) = act ? 1 : 0;
     any = any || act;
   }
   if (!any) return;
   // generator space: v0 = G q_free, Lambda = G Z^-1 G^T (column block by column block)
-  for (int g = 0; g < NG; ++g) AT(b.fv0, g) = artic_gen_value(m, b, w, g, 0, b.fq);
+  for (int g = 0; g < NG; ++g) FT(b.fv0, g) = artic_gen_value(m, b, w, g, 0, b.fq);
   for (int gi = 0; gi < m.ngen; ++gi) {
     artic_solve_generators<6>(m, b, w, m.gen_body[gi], -1);
     for (int r = 0; r < 6; ++r)
-      for (int g = 0; g < NG; ++g) AT(b.fLam, g * NG + 6 * gi + r) = artic_gen_value(m, b, w, g, r, b.ax);
+      for (int g = 0; g < NG; ++g) FT(b.fLam, g * NG + 6 * gi + r) = artic_gen_value(m, b, w, g, r, b.ax);
   }
   for (int h = 6 * m.ngen; h < NG; ++h) {
     const int k = m.glimdof[h - 6 * m.ngen];
     artic_solve_generators<1>(m, b, w, m.dofbody[k], k);
-    for (int g = 0; g < NG; ++g) AT(b.fLam, g * NG + h) = artic_gen_value(m, b, w, g, 0, b.ax);
+    for (int g = 0; g < NG; ++g) FT(b.fLam, g * NG + h) = artic_gen_value(m, b, w, g, 0, b.ax);
   }
 }
 
 // ---------------------------------------------------------------------------------------
 // Gauss-Seidel in generator space, one world per lane.
+//
+// The generator rows of ONE body (or one limited dof) are kept in registers while the sweep
+// visits the constraints attached to it: u_F (its twist), Lambda_FF (its 6x6 diagonal block)
+// and dy_F (the wrench accumulated since the block was loaded).  Rows outside the block are
+// brought up to date lazily, when the sweep moves to another body:
+//     u[r] += Lambda[r, F] dy_F ,   y[F] += dy_F .
+// For human36 the sweep order is 4 contacts of the right foot, 4 of the left foot, 2 knee
+// limits (registration order, core.py:929-935): two block switches per sweep instead of a
+// 14x6 update through memory per constraint.
+struct GsCache {
+  int g, n;          // first generator row of the cached block and its size (6 or 1); g < 0: empty
+  double u[6], dy[6], L[36];
+};
+
+ARB_D void gs_cache_flush(const DevModel& m, const DevBatch& b, int64_t w, GsCache& k) {
+  const int NG = m.ngrows;
+  if (k.g < 0) return;
+  bool any = false;
+#pragma unroll
+  for (int p = 0; p < 6; ++p) any = any || (p < k.n && k.dy[p] != 0.);
+  if (any) {
+    for (int r = 0; r < NG; ++r) {
+      if (r >= k.g && r < k.g + k.n) continue;
+      double acc = 0.;
+#pragma unroll
+      for (int p = 0; p < 6; ++p)
+        if (p < k.n) acc += FT(b.fLam, r * NG + k.g + p) * k.dy[p];
+      FT(b.fu, r) += acc;
+    }
+#pragma unroll
+    for (int p = 0; p < 6; ++p)
+      if (p < k.n) FT(b.fy, k.g + p) += k.dy[p];
+  }
+#pragma unroll
+  for (int p = 0; p < 6; ++p)
+    if (p < k.n) FT(b.fu, k.g + p) = k.u[p];
+  k.g = -1;
+}
+
+template <bool WITH_U>
+ARB_D void gs_cache_load(const DevModel& m, const DevBatch& b, int64_t w, GsCache& k, int g, int n) {
+  const int NG = m.ngrows;
+  k.g = g;
+  k.n = n;
+#pragma unroll
+  for (int p = 0; p < 6; ++p) {
+    k.dy[p] = 0.;
+    k.u[p] = (WITH_U && p < n) ? FT(b.fu, g + p) : 0.;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) k.L[6 * p + q] = (p < n && q < n) ? FT(b.fLam, (g + p) * NG + g + q) : 0.;
+  }
+}
+
+// one visit of a constraint that touches TWO generator bodies (e.g. a ball-and-socket joint
+// between two moving bodies): everything through memory.
+ARB_D void gs_visit_two_body(const DevModel& m, const DevBatch& b, int64_t w, int c, double dt, int* status) {
+  const int NG = m.ngrows;
+  const int type = m.ctype[c];
+  const double* cd = m.cdbl + ARB_CONS_NDBL * c;
+  const int r0 = m.crow[c];
+  const int g1 = m.cgen1[c], g0 = m.cgen0[c];
+  const int nd = arb_cons_ndol(type);
+  double v[4], f[4], df[4];
+  for (int i = 0; i < nd; ++i) {
+    double acc = 0.;
+    if (g1 >= 0)
+#pragma unroll
+      for (int p = 0; p < 6; ++p) acc += FT(b.fT1, c * 24 + i * 6 + p) * FT(b.fu, g1 + p);
+    if (g0 >= 0)
+#pragma unroll
+      for (int p = 0; p < 6; ++p) acc -= FT(b.fT0, c * 24 + i * 6 + p) * FT(b.fu, g0 + p);
+    v[i] = acc;
+    f[i] = FT(b.ff, r0 + i);
+  }
+  if (type == ARB_CONS_BALL_SOCKET) {
+    double rhs3[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) rhs3[i] = v[i] + FT(b.faux, 4 * c + i) / dt;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double t = 0.;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) t += FT(b.fP, r0 * 4 + 3 * i + j) * rhs3[j];
+      df[i] = -t;
+      FT(b.ff, r0 + i) = f[i] + df[i];
+    }
+  } else {
+    double A4[16], P4[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { A4[i] = FT(b.fAcc, r0 * 4 + i); P4[i] = FT(b.fP, r0 * 4 + i); }
+    const int br = softfinger_solve(v, A4, P4, FT(b.faux, 4 * c), cd[36], cd + 37, dt, f, df, status);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) FT(b.ff, r0 + i) = f[i];
+    FT(b.fbranch, c) = br;
+  }
+  // y += T^T df ; u += Lambda[:, g..g+5] (T^T df)
+  for (int s = 0; s < 2; ++s) {
+    const int gs = s ? g0 : g1;
+    if (gs < 0) continue;
+    const double* Ts = s ? b.fT0 : b.fT1;
+    const double sign = s ? -1. : 1.;
+    double wv[6];
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      double acc = 0.;
+      for (int i = 0; i < nd; ++i) acc += FT(Ts, c * 24 + i * 6 + p) * df[i];
+      wv[p] = sign * acc;
+      FT(b.fy, gs + p) += wv[p];
+    }
+    for (int g = 0; g < NG; ++g) {
+      double acc = 0.;
+#pragma unroll
+      for (int p = 0; p < 6; ++p) acc += FT(b.fLam, g * NG + gs + p) * wv[p];
+      FT(b.fu, g) += acc;
+    }
+  }
+}
+
+// one visit of a constraint whose rows depend on ONE generator body (the other frame is on
+// the ground): ND rows, block in the cache
+template <int ND>
+ARB_D void gs_visit_one_body(const DevModel& m, const DevBatch& b, int64_t w, int c, double dt,
+                             GsCache& k, int* status) {
+  const int type = m.ctype[c];
+  const double* cd = m.cdbl + ARB_CONS_NDBL * c;
+  const int r0 = m.crow[c];
+  const bool side0 = m.cgen1[c] < 0;          // the moving body is body0: rows enter with a minus sign
+  const double* Tp = (side0 ? b.fT0 : b.fT1) + c * (24 * ARB_TILE);
+  const double sign = side0 ? -1. : 1.;
+  double T[ND * 6];
+#pragma unroll
+  for (int i = 0; i < ND * 6; ++i) T[i] = sign * Tp[i * ARB_TILE];
+  double v[ND], f[ND], df[ND];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    double acc = 0.;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) acc += T[i * 6 + p] * k.u[p];
+    v[i] = acc;
+    f[i] = FT(b.ff, r0 + i);
+  }
+  if (ND == 3) {
+    double rhs3[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) rhs3[i] = v[i] + FT(b.faux, 4 * c + i) / dt;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      double t = 0.;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) t += FT(b.fP, r0 * 4 + 3 * i + j) * rhs3[j];
+      df[i] = -t;
+      FT(b.ff, r0 + i) = f[i] + df[i];
+    }
+  } else {
+    double A4[16], P4[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { A4[i] = FT(b.fAcc, r0 * 4 + i); P4[i] = FT(b.fP, r0 * 4 + i); }
+    const int br = softfinger_solve(v, A4, P4, FT(b.faux, 4 * c), cd[36], cd + 37, dt, f, df, status);
+#pragma unroll
+    for (int i = 0; i < ND; ++i) FT(b.ff, r0 + i) = f[i];
+    FT(b.fbranch, c) = br;
+  }
+  double wv[6];
+#pragma unroll
+  for (int p = 0; p < 6; ++p) {
+    double acc = 0.;
+#pragma unroll
+    for (int i = 0; i < ND; ++i) acc += T[i * 6 + p] * df[i];
+    wv[p] = acc;
+    k.dy[p] += acc;
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    double acc = 0.;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) acc += k.L[6 * q + p] * wv[p];
+    k.u[q] += acc;
+  }
+}
+
+// diagonal Delassus block A_cc = T Lambda_FF T^T of a one-body constraint and its pseudo-inverse
+template <int ND>
+ARB_D void gs_diag_one_body(const DevModel& m, const DevBatch& b, int64_t w, int c, const GsCache& k) {
+  const int r0 = m.crow[c];
+  const double* Tp = ((m.cgen1[c] < 0) ? b.fT0 : b.fT1) + c * (24 * ARB_TILE);
+  double T[ND * 6], A[ND * ND], P[ND * ND];
+#pragma unroll
+  for (int i = 0; i < ND * 6; ++i) T[i] = Tp[i * ARB_TILE];
+#pragma unroll
+  for (int i = 0; i < ND; ++i) {
+    double tl[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+      double acc = 0.;
+#pragma unroll
+      for (int p = 0; p < 6; ++p) acc += T[i * 6 + p] * k.L[6 * p + q];
+      tl[q] = acc;
+    }
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      double acc = 0.;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) acc += tl[q] * T[j * 6 + q];
+      A[i * ND + j] = acc;
+    }
+  }
+  pinv_small<ND>(A, P);
+#pragma unroll
+  for (int i = 0; i < ND * ND; ++i) { FT(b.fAcc, r0 * 4 + i) = A[i]; FT(b.fP, r0 * 4 + i) = P[i]; }
+}
+
 ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, double dt) {
-  const int64_t W = b.W;
   const int NG = m.ngrows;
   int status = 0;
   bool any = false;
-  for (int c = 0; c < m.nc; ++c) any = any || AT(b.factive, c);
-  for (int g = 0; g < NG; ++g) AT(b.fy, g) = 0.;
+  for (int c = 0; c < m.nc; ++c) any = any || FT(b.factive, c);
+  for (int g = 0; g < NG; ++g) FT(b.fy, g) = 0.;
   if (!any) return;
+  // constraint forces live in tiled scratch during the sweeps (ball-and-socket rows carry
+  // the warm start, the others were reset by the prepare stage)
+  for (int r = 0; r < m.nrows; ++r) FT(b.ff, r) = ST(b.cforce, r);
+  GsCache k;
+  k.g = -1;
+  k.n = 0;
   // y0 = sum T_c^T f_c (warm start of ball-and-socket forces), diagonal blocks and pinv
+  bool warm = false;
   for (int c = 0; c < m.nc; ++c) {
-    if (!AT(b.factive, c)) continue;
+    if (!FT(b.factive, c)) continue;
     const int type = m.ctype[c];
     const int nd = arb_cons_ndol(type);
     const int r0 = m.crow[c];
     const int g1 = m.cgen1[c], g0 = m.cgen0[c];
     if (type == ARB_CONS_JOINT_LIMITS) {
-      const double a = AT(b.fLam, g1 * NG + g1);
+      const double a = FT(b.fLam, g1 * NG + g1);
       double p;
       pinv_small<1>(&a, &p);
-      AT(b.fAcc, r0 * 4) = a;
-      AT(b.fP, r0 * 4) = p;
-      AT(b.fy, g1) += AT(b.cforce, r0);
+      FT(b.fAcc, r0 * 4) = a;
+      FT(b.fP, r0 * 4) = p;
+      const double f0 = FT(b.ff, r0);
+      if (f0 != 0.) { FT(b.fy, g1) += f0; warm = true; }
       continue;
     }
-    // A_cc = sum over sides s,t of  sign * T_s Lambda[g_s, g_t] T_t^T
-    double A[16];
-    for (int i = 0; i < nd * nd; ++i) A[i] = 0.;
-    for (int s = 0; s < 2; ++s) {
-      const int gs = s ? g0 : g1;
-      if (gs < 0) continue;
-      const double* Ts = s ? b.fT0 : b.fT1;
-      for (int t = 0; t < 2; ++t) {
-        const int gt = t ? g0 : g1;
-        if (gt < 0) continue;
-        const double* Tt = t ? b.fT0 : b.fT1;
-        const double sign = (s == t) ? 1. : -1.;
-        for (int i = 0; i < nd; ++i) {
-          double tl[6];  // row i of T_s Lambda[gs.., gt..]
+    if (g1 < 0 || g0 < 0) {
+      const int gF = g1 < 0 ? g0 : g1;
+      if (k.g != gF) gs_cache_load<false>(m, b, w, k, gF, 6);
+      if (nd == 3) gs_diag_one_body<3>(m, b, w, c, k); else gs_diag_one_body<4>(m, b, w, c, k);
+    } else {
+      // A_cc = sum over sides s,t of  sign * T_s Lambda[g_s, g_t] T_t^T
+      double A[16];
+      for (int i = 0; i < nd * nd; ++i) A[i] = 0.;
+      for (int s = 0; s < 2; ++s) {
+        const int gs = s ? g0 : g1;
+        const double* Ts = s ? b.fT0 : b.fT1;
+        for (int t = 0; t < 2; ++t) {
+          const int gt = t ? g0 : g1;
+          const double* Tt = t ? b.fT0 : b.fT1;
+          const double sign = (s == t) ? 1. : -1.;
+          for (int i = 0; i < nd; ++i) {
+            double tl[6];  // row i of T_s Lambda[gs.., gt..]
 #pragma unroll
-          for (int q = 0; q < 6; ++q) {
-            double acc = 0.;
+            for (int q = 0; q < 6; ++q) {
+              double acc = 0.;
 #pragma unroll
-            for (int p = 0; p < 6; ++p) acc += AT(Ts, c * 24 + i * 6 + p) * AT(b.fLam, (gs + p) * NG + gt + q);
-            tl[q] = acc;
-          }
-          for (int j = 0; j < nd; ++j) {
-            double acc = 0.;
+              for (int p = 0; p < 6; ++p) acc += FT(Ts, c * 24 + i * 6 + p) * FT(b.fLam, (gs + p) * NG + gt + q);
+              tl[q] = acc;
+            }
+            for (int j = 0; j < nd; ++j) {
+              double acc = 0.;
 #pragma unroll
-            for (int q = 0; q < 6; ++q) acc += tl[q] * AT(Tt, c * 24 + j * 6 + q);
-            A[i * nd + j] += sign * acc;
+              for (int q = 0; q < 6; ++q) acc += tl[q] * FT(Tt, c * 24 + j * 6 + q);
+              A[i * nd + j] += sign * acc;
+            }
           }
         }
       }
+      double P[16];
+      if (nd == 3) pinv_small<3>(A, P); else pinv_small<4>(A, P);
+      for (int i = 0; i < nd * nd; ++i) { FT(b.fAcc, r0 * 4 + i) = A[i]; FT(b.fP, r0 * 4 + i) = P[i]; }
     }
-    double P[16];
-    if (nd == 3) pinv_small<3>(A, P); else pinv_small<4>(A, P);
-    for (int i = 0; i < nd * nd; ++i) { AT(b.fAcc, r0 * 4 + i) = A[i]; AT(b.fP, r0 * 4 + i) = P[i]; }
-    for (int s = 0; s < 2; ++s) {
-      const int gs = s ? g0 : g1;
-      if (gs < 0) continue;
-      const double* Ts = s ? b.fT0 : b.fT1;
-      const double sign = s ? -1. : 1.;
+    if (type == ARB_CONS_BALL_SOCKET) {   // the only forces that persist across steps
+      for (int s = 0; s < 2; ++s) {
+        const int gs = s ? g0 : g1;
+        if (gs < 0) continue;
+        const double* Ts = s ? b.fT0 : b.fT1;
+        const double sign = s ? -1. : 1.;
 #pragma unroll
-      for (int p = 0; p < 6; ++p) {
-        double acc = 0.;
-        for (int i = 0; i < nd; ++i) acc += AT(Ts, c * 24 + i * 6 + p) * AT(b.cforce, r0 + i);
-        AT(b.fy, gs + p) += sign * acc;
+        for (int p = 0; p < 6; ++p) {
+          double acc = 0.;
+          for (int i = 0; i < nd; ++i) acc += FT(Ts, c * 24 + i * 6 + p) * FT(b.ff, r0 + i);
+          FT(b.fy, gs + p) += sign * acc;
+        }
       }
+      warm = true;
     }
   }
+  k.g = -1;
   // u = v0 + Lambda y0
   for (int g = 0; g < NG; ++g) {
-    double t = AT(b.fv0, g);
-    for (int h = 0; h < NG; ++h) {
-      const double yh = AT(b.fy, h);
-      if (yh != 0.) t += AT(b.fLam, g * NG + h) * yh;
-    }
-    AT(b.fu, g) = t;
+    double t = FT(b.fv0, g);
+    if (warm)
+      for (int h = 0; h < NG; ++h) {
+        const double yh = FT(b.fy, h);
+        if (yh != 0.) t += FT(b.fLam, g * NG + h) * yh;
+      }
+    FT(b.fu, g) = t;
   }
   for (int sweep = 0; sweep < ARB_GS_SWEEPS; ++sweep) {
     for (int c = 0; c < m.nc; ++c) {
-      if (!AT(b.factive, c)) continue;
+      if (!FT(b.factive, c)) continue;
       const int type = m.ctype[c];
-      const double* cd = m.cdbl + ARB_CONS_NDBL * c;
-      const int r0 = m.crow[c];
       const int g1 = m.cgen1[c], g0 = m.cgen0[c];
       if (type == ARB_CONS_JOINT_LIMITS) {
-        const double a = AT(b.fAcc, r0 * 4), p = AT(b.fP, r0 * 4);
-        const double f = AT(b.cforce, r0), v = AT(b.fu, g1), q = AT(b.faux, 4 * c);
+        const double* cd = m.cdbl + ARB_CONS_NDBL * c;
+        const int r0 = m.crow[c];
+        if (k.g != g1) {
+          gs_cache_flush(m, b, w, k);
+          gs_cache_load<true>(m, b, w, k, g1, 1);
+        }
+        const double a = FT(b.fAcc, r0 * 4), p = FT(b.fP, r0 * 4);
+        const double f = FT(b.ff, r0), v = k.u[0], q = FT(b.faux, 4 * c);
         const double pred = q + dt * (v - a * f);
         double nf;
         int br;
@@ -258,81 +504,38 @@ ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, doubl
         else if (cd[1] <= pred) { nf = p * ((cd[1] - pred) / dt); br = 3; }
         else { nf = 0.; br = 1; }
         const double df = nf - f;
-        AT(b.cforce, r0) = nf;
-        AT(b.fbranch, c) = br;
+        FT(b.ff, r0) = nf;
+        FT(b.fbranch, c) = br;
         if (df != 0.) {
-          AT(b.fy, g1) += df;
-          for (int g = 0; g < NG; ++g) AT(b.fu, g) += AT(b.fLam, g * NG + g1) * df;
+          k.dy[0] += df;
+          k.u[0] += k.L[0] * df;
         }
         continue;
       }
-      const int nd = arb_cons_ndol(type);
-      // constraint velocity from the generator velocities
-      double v[4], f[4], df[4];
-      for (int i = 0; i < nd; ++i) {
-        double acc = 0.;
-        if (g1 >= 0)
-#pragma unroll
-          for (int p = 0; p < 6; ++p) acc += AT(b.fT1, c * 24 + i * 6 + p) * AT(b.fu, g1 + p);
-        if (g0 >= 0)
-#pragma unroll
-          for (int p = 0; p < 6; ++p) acc -= AT(b.fT0, c * 24 + i * 6 + p) * AT(b.fu, g0 + p);
-        v[i] = acc;
-        f[i] = AT(b.cforce, r0 + i);
+      if (g1 >= 0 && g0 >= 0) {
+        gs_cache_flush(m, b, w, k);
+        gs_visit_two_body(m, b, w, c, dt, &status);
+        continue;
       }
-      if (type == ARB_CONS_BALL_SOCKET) {
-        double rhs3[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) rhs3[i] = v[i] + AT(b.faux, 4 * c + i) / dt;
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          double t = 0.;
-#pragma unroll
-          for (int j = 0; j < 3; ++j) t += AT(b.fP, r0 * 4 + 3 * i + j) * rhs3[j];
-          df[i] = -t;
-          AT(b.cforce, r0 + i) = f[i] + df[i];
-        }
-      } else {
-        double A4[16], P4[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) { A4[i] = AT(b.fAcc, r0 * 4 + i); P4[i] = AT(b.fP, r0 * 4 + i); }
-        const int br = softfinger_solve(v, A4, P4, AT(b.faux, 4 * c), cd[36], cd + 37, dt, f, df, &status);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) AT(b.cforce, r0 + i) = f[i];
-        AT(b.fbranch, c) = br;
+      const int gF = g1 < 0 ? g0 : g1;
+      if (k.g != gF) {
+        gs_cache_flush(m, b, w, k);
+        gs_cache_load<true>(m, b, w, k, gF, 6);
       }
-      // y += T^T df ; u += Lambda[:, g..g+5] (T^T df)
-      for (int s = 0; s < 2; ++s) {
-        const int gs = s ? g0 : g1;
-        if (gs < 0) continue;
-        const double* Ts = s ? b.fT0 : b.fT1;
-        const double sign = s ? -1. : 1.;
-        double wv[6];
-#pragma unroll
-        for (int p = 0; p < 6; ++p) {
-          double acc = 0.;
-          for (int i = 0; i < nd; ++i) acc += AT(Ts, c * 24 + i * 6 + p) * df[i];
-          wv[p] = sign * acc;
-          AT(b.fy, gs + p) += wv[p];
-        }
-        for (int g = 0; g < NG; ++g) {
-          double acc = 0.;
-#pragma unroll
-          for (int p = 0; p < 6; ++p) acc += AT(b.fLam, g * NG + gs + p) * wv[p];
-          AT(b.fu, g) += acc;
-        }
-      }
+      if (type == ARB_CONS_BALL_SOCKET) gs_visit_one_body<3>(m, b, w, c, dt, k, &status);
+      else gs_visit_one_body<4>(m, b, w, c, dt, k, &status);
     }
   }
+  gs_cache_flush(m, b, w, k);
+  for (int r = 0; r < m.nrows; ++r) ST(b.cforce, r) = FT(b.ff, r);
   if (status) b.status[w] |= status;
 }
 
 // ---------------------------------------------------------------------------------------
 ARB_D void world_fused_finish(const DevModel& m, const DevBatch& b, int64_t w, double dt) {
-  const int64_t W = b.W;
   const int n = m.ndof;
   bool any = false;
-  for (int c = 0; c < m.nc; ++c) any = any || AT(b.factive, c);
+  for (int c = 0; c < m.nc; ++c) any = any || FT(b.factive, c);
   // q'+ = q_free + Z^-1 G^T y
   if (any) {
     artic_backward_wrenches(m, b, w, b.fy);
@@ -340,9 +543,9 @@ ARB_D void world_fused_finish(const DevModel& m, const DevBatch& b, int64_t w, d
   }
   bool finite = true;
   for (int i = 0; i < n; ++i) {
-    double t = AT(b.fq, i);
-    if (any) t += AT(b.ax, i);
-    AT(b.gvel, i) = t;
+    double t = FT(b.fq, i);
+    if (any) t += FT(b.ax, i);
+    ST(b.gvel, i) = t;
     finite = finite && isfinite(t);
   }
   for (int j = 0; j < m.nj; ++j) {
@@ -350,9 +553,9 @@ ARB_D void world_fused_finish(const DevModel& m, const DevBatch& b, int64_t w, d
     const int g = m.jgpos[j], d = m.jdof[j];
     if (type == ARB_JOINT_FREE) {
       double q[16], tw[6];
-      for (int i = 0; i < 16; ++i) q[i] = AT(b.gpos, g + i);
+      for (int i = 0; i < 16; ++i) q[i] = ST(b.gpos, g + i);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) tw[i] = dt * AT(b.gvel, d + i);
+      for (int i = 0; i < 6; ++i) tw[i] = dt * ST(b.gvel, d + i);
       Se3 H, E, R;
       se3_from16(q, H);
       se3_exp(tw, E);
@@ -360,12 +563,12 @@ ARB_D void world_fused_finish(const DevModel& m, const DevBatch& b, int64_t w, d
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) AT(b.gpos, g + 4 * r + c) = R.R[3 * r + c];
-        AT(b.gpos, g + 4 * r + 3) = R.p[r];
+        for (int c = 0; c < 3; ++c) ST(b.gpos, g + 4 * r + c) = R.R[3 * r + c];
+        ST(b.gpos, g + 4 * r + 3) = R.p[r];
       }
     } else {
       const int nd = arb_joint_ndof(type);
-      for (int i = 0; i < nd; ++i) AT(b.gpos, g + i) += dt * AT(b.gvel, d + i);
+      for (int i = 0; i < nd; ++i) ST(b.gpos, g + i) += dt * ST(b.gvel, d + i);
     }
   }
   if (!finite) b.status[w] |= ARB_STATUS_NONFINITE;

@@ -229,10 +229,10 @@ static inline ScratchSizes scratch_sizes(const HostModel& m) {
   return s;
 }
 struct FusedSizes {
-  int64_t fq, fLam, fv0, fT1, fT0, fu, fy, fAcc, fP, faux, fpose, factive, fbranch;
+  int64_t fq, fLam, fv0, fT1, fT0, fu, fy, fAcc, fP, faux, fpose, ff, factive, fbranch;
   int64_t aX, atw, ath, aS, aSh, aU, aLA, aLM, adinv, aIA, aIM, abeta, au, ax, aV;
   int64_t total_doubles() const {
-    return fq + fLam + fv0 + fT1 + fT0 + fu + fy + fAcc + fP + faux + fpose +
+    return fq + fLam + fv0 + fT1 + fT0 + fu + fy + fAcc + fP + faux + fpose + ff +
            aX + atw + ath + aS + aSh + aU + aLA + aLM + adinv + aIA + aIM + abeta + au + ax + aV;
   }
   int64_t total_ints() const { return factive + fbranch; }
@@ -243,26 +243,33 @@ static inline FusedSizes fused_sizes(const HostModel& m) {
                 nr = m.nrows > 0 ? m.nrows : 1;
   const int64_t nj = m.nj > 0 ? m.nj : 1, nn = n > 0 ? n : 1;
   s.fq = nn; s.fLam = NG * NG; s.fv0 = NG; s.fT1 = nc * 24; s.fT0 = nc * 24;
-  s.fu = NG; s.fy = NG; s.fAcc = nr * 4; s.fP = nr * 4; s.faux = nc * 4; s.fpose = nj * 12;
+  s.fu = NG; s.fy = NG; s.fAcc = nr * 4; s.fP = nr * 4; s.faux = nc * 4; s.fpose = nj * 12; s.ff = nr;
   s.factive = nc; s.fbranch = nc;
   s.aX = nj * 12; s.atw = nj * 6; s.ath = nj * 6;
   s.aS = s.aSh = s.aU = s.aLA = s.aLM = nn * 6; s.adinv = nn;
   s.aIA = s.aIM = nj * 36; s.abeta = nj * 6; s.au = 6 * nn; s.ax = 6 * nn; s.aV = nj * 72;
   return s;
 }
-static inline void carve_fused(const FusedSizes& s, int64_t W, double* dbl, int* ints, DevBatch& b) {
+// Tiled layout: tile t of ARB_TILE worlds owns doubles [t*R*ARB_TILE, (t+1)*R*ARB_TILE), array X
+// starts offX*ARB_TILE into the tile; the pointers stored here are those of tile 0 (the kernels
+// add the per-thread tile offset, fused_tile_view).  Allocate for fused_padded_worlds(W).
+static inline int64_t fused_padded_worlds(int64_t W) { return (W + ARB_TILE - 1) / ARB_TILE * ARB_TILE; }
+static inline void carve_fused(const FusedSizes& s, double* dbl, int* ints, DevBatch& b) {
   double* p = dbl;
-  auto take = [&](int64_t k) { double* r = p; p += k * W; return r; };
+  auto take = [&](int64_t k) { double* r = p; p += k * ARB_TILE; return r; };
   b.fq = take(s.fq); b.fLam = take(s.fLam); b.fv0 = take(s.fv0);
   b.fT1 = take(s.fT1); b.fT0 = take(s.fT0); b.fu = take(s.fu); b.fy = take(s.fy);
   b.fAcc = take(s.fAcc); b.fP = take(s.fP); b.faux = take(s.faux); b.fpose = take(s.fpose);
+  b.ff = take(s.ff);
   b.aX = take(s.aX); b.atw = take(s.atw); b.ath = take(s.ath);
   b.aS = take(s.aS); b.aSh = take(s.aSh); b.aU = take(s.aU); b.aLA = take(s.aLA); b.aLM = take(s.aLM);
   b.adinv = take(s.adinv); b.aIA = take(s.aIA); b.aIM = take(s.aIM); b.abeta = take(s.abeta);
   b.au = take(s.au); b.ax = take(s.ax); b.aV = take(s.aV);
   int* q = ints;
-  auto takei = [&](int64_t k) { int* r = q; q += k * W; return r; };
+  auto takei = [&](int64_t k) { int* r = q; q += k * ARB_TILE; return r; };
   b.factive = takei(s.factive); b.fbranch = takei(s.fbranch);
+  b.frec = s.total_doubles();
+  b.firec = s.total_ints();
 }
 // carve `dbl` (doubles) and `ints` into the DevBatch members; W worlds
 static inline void carve_scratch(const ScratchSizes& s, int64_t W, double* dbl, int* ints, DevBatch& b) {

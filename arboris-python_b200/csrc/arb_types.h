@@ -18,6 +18,8 @@ ARB_HDI int arb_cons_ndol(int t) {
   return t == ARB_CONS_JOINT_LIMITS ? 1 : t == ARB_CONS_BALL_SOCKET ? 3 : 4;
 }
 
+#define ARB_TILE 32          /* worlds per tile of the fused scratch ([W/32][elem][32]) */
+
 #define ARB_BODY_MASSIVE 1   /* some entry of the mass matrix > 0 (WeightController.init, controllers.py:37) */
 #define ARB_BODY_HASMASS 2   /* mass matrix not identically zero */
 #define ARB_BODY_HASVISC 4   /* viscosity matrix not identically zero */
@@ -68,7 +70,8 @@ struct DevModel {
   int nweight;
 };
 
-// Per-batch memory: caller-owned state + library-owned scratch, all [elem][W].
+// Per-batch memory: caller-owned state and the phase-API scratch are [elem][W]; the fused
+// scratch (f*, a*) is tiled [W/32][elem][32].
 struct DevBatch {
   int64_t W;
   double *gpos, *gvel, *cforce;        // state (bound)
@@ -100,7 +103,9 @@ struct DevBatch {
   double *fAcc, *fP; // [nrows][4] diagonal Delassus blocks and their pseudo-inverses
   double *faux;      // [nc][4]
   double *fpose;     // [nj][12]   body poses (for contacts and gravity)
+  double *ff;        // [nrows]    constraint forces during the sweeps
   int *factive, *fbranch;  // [nc]
+  int64_t frec, firec;     // doubles / ints per world in the tiled fused scratch
   // ---- articulated-body factorisation of Z (arb_artic.cuh), [elem][W] ------------------
   double *aX;        // [nj][12]   H_pc of each joint
   double *atw, *ath; // [nj][6]    body twist T_b and the accumulated joint term theta_b

@@ -60,9 +60,9 @@ void* ht_create(const arb_model_desc* d, int64_t W, char* errbuf, int errlen) {
   carve_scratch(s, W, hb->dbl.data(), hb->ints.data(), hb->b);
   hb->b.status = hb->status.data();
   FusedSizes fs = fused_sizes(hb->hm);
-  hb->fdbl.assign(fs.total_doubles() * W, 0.);
-  hb->fints.assign(fs.total_ints() * W, 0);
-  carve_fused(fs, W, hb->fdbl.data(), hb->fints.data(), hb->b);
+  hb->fdbl.assign(fs.total_doubles() * fused_padded_worlds(W), 0.);
+  hb->fints.assign(fs.total_ints() * fused_padded_worlds(W), 0);
+  carve_fused(fs, hb->fdbl.data(), hb->fints.data(), hb->b);
   return hb;
 }
 void ht_destroy(void* p) { delete (HostBatch*)p; }
@@ -90,9 +90,10 @@ void ht_integrate(void* p, double dt) {
 void ht_fused_step(void* p, double dt) {
   HostBatch* hb = (HostBatch*)p;
   for (int64_t w = 0; w < hb->b.W; ++w) {
-    world_fused_prepare(hb->dm, hb->b, w, dt);
-    world_fused_gs(hb->dm, hb->b, w, dt);
-    world_fused_finish(hb->dm, hb->b, w, dt);
+    const DevBatch t = fused_tile_view(hb->b, w);
+    world_fused_prepare(hb->dm, t, w, dt);
+    world_fused_gs(hb->dm, t, w, dt);
+    world_fused_finish(hb->dm, t, w, dt);
   }
 }
 // raw scratch access: which = index into the DevBatch double members in declaration order
@@ -107,13 +108,22 @@ double* ht_array(void* p, const char* name) {
   if (s == "caux") return b.caux;
   return nullptr;
 }
+// fused int outputs are tiled: copy out as [elem][W]
+void ht_fused_ints(void* p, const char* name, int nelem, int* out) {
+  HostBatch* hb = (HostBatch*)p;
+  const std::string s(name);
+  const int* base = s == "factive" ? hb->b.factive : hb->b.fbranch;
+  for (int64_t w = 0; w < hb->b.W; ++w) {
+    const int* t = base + (w / ARB_TILE) * hb->b.firec * ARB_TILE + w % ARB_TILE;
+    for (int e = 0; e < nelem; ++e) out[e * hb->b.W + w] = t[e * ARB_TILE];
+  }
+}
 int* ht_iarray(void* p, const char* name) {
   HostBatch* hb = (HostBatch*)p;
   DevBatch& b = hb->b;
   std::string s(name);
   if (s == "cactive") return b.cactive; if (s == "cbranch") return b.cbranch; if (s == "cdol") return b.cdol;
   if (s == "czidx") return b.czidx; if (s == "status") return b.status;
-  if (s == "factive") return b.factive; if (s == "fbranch") return b.fbranch;
   return nullptr;
 }
 void ht_pinv(int n, const double* a, double* out) {

@@ -45,6 +45,7 @@ def lib():
         L.ht_array.argtypes = [C.c_void_p, C.c_char_p]
         L.ht_iarray.restype = C.POINTER(C.c_int)
         L.ht_iarray.argtypes = [C.c_void_p, C.c_char_p]
+        L.ht_fused_ints.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -89,6 +90,11 @@ class HostBatch(object):
         return np.ctypeslib.as_array(p, shape=(n * self.W,)).reshape(shape + (self.W,))
 
     def iarr(self, name, *shape):
+        if name in ("factive", "fbranch"):      # tiled fused scratch: copied out as [elem][W]
+            n = int(np.prod(shape))
+            out = np.zeros((n, self.W), dtype=np.int32)
+            self.L.ht_fused_ints(self.h, name.encode(), n, out.ctypes.data_as(C.POINTER(C.c_int)))
+            return out.reshape(shape + (self.W,))
         p = self.L.ht_iarray(self.h, name.encode())
         n = int(np.prod(shape))
         return np.ctypeslib.as_array(p, shape=(n * self.W,)).reshape(shape + (self.W,))
