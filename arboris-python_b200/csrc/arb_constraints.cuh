@@ -80,6 +80,64 @@ ARB_D void write_frame_pair_jac(const DevModel& m, const DevBatch& b, int64_t w,
   }
 }
 
+// Sliding branch of SoftFingerContact.solve (constraints.py:803-836): s = smallest real
+// eigenvalue <= 0 of B (with the reference's scalar inner products), then
+// newf = (A - s diag(eps^-2, 0))^-1 (-alpha).
+ARB_NOINLINE void softfinger_sliding(const double* A, const double* alpha, double mu, const double* eps,
+                              double* newf, int* status) {
+  double s = 0.;
+  bool found = false;
+  const bool unit_eps = (eps[0] == 1. && eps[1] == 1. && eps[2] == 1.);
+  if (!(unit_eps && sliding_root_structured(A, alpha, mu, &s, &found))) {
+    const double Yc[3] = {A[3], A[7], A[11]};
+    const double yn = A[15];
+    double beta[3], bb[3];
+    const double a = mu / yn * alpha[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      beta[i] = alpha[i] - alpha[3] / yn * Yc[i];
+      bb[i] = mu / yn * Yc[i];
+    }
+    const double ycyc = Yc[0] * Yc[0] + Yc[1] * Yc[1] + Yc[2] * Yc[2];
+    const double betab = beta[0] * bb[0] + beta[1] * bb[1] + beta[2] * bb[2];
+    const double betabeta = beta[0] * beta[0] + beta[1] * beta[1] + beta[2] * beta[2];
+    const double bdotb = bb[0] * bb[0] + bb[1] * bb[1] + bb[2] * bb[2];
+    double Bm[36];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const double e2 = eps[i] * eps[i];
+        const double yhat = A[4 * i + j] - ycyc / yn;
+        Bm[6 * (3 + i) + 3 + j] = e2 * yhat;
+        Bm[6 * i + j] = e2 * (yhat + 2. / a * betab);
+        // dot(E, scalar) is E*scalar in numpy: these two blocks are DIAGONAL
+        Bm[6 * i + 3 + j] = (i == j) ? -(e2 * (betabeta / (a * a))) : 0.;
+        Bm[6 * (3 + i) + j] = (i == j) ? e2 * bdotb - 1. : 0.;
+      }
+    double wr[6], wi[6];
+    if (!eig_real_general6(Bm, wr, wi)) *status |= ARB_STATUS_EIG_NOCONV;
+    found = false;
+    s = 0.;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (wi[i] == 0. && wr[i] <= 0.) {
+        if (!found || wr[i] < s) s = wr[i];
+        found = true;
+      }
+  }
+  if (!found) { s = -1e10; *status |= ARB_STATUS_EIG_NOROOT; }
+  if (s < -1e10) s = -1e10;
+  double A2[16], nalpha[4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) A2[i] = A[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) A2[5 * i] -= s * (1. / (eps[i] * eps[i]));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) nalpha[i] = -alpha[i];
+  if (!solve_small<4>(A2, nalpha, newf)) *status |= ARB_STATUS_SINGULAR;
+}
+
 // SoftFingerContact.solve (constraints.py:780-836).  v: constraint velocity (4),
 // A: 4x4 diagonal block of the Delassus operator, P: its pseudo-inverse, f: force
 // (updated), df: returned increment.  Returns the branch id.
@@ -119,60 +177,9 @@ ARB_D int softfinger_solve(const double* v, const double* A, const double* P, do
     for (int i = 0; i < 4; ++i) f[i] = nf[i];
     return 2;
   }
-  // sliding: s = smallest real eigenvalue <= 0 of B (with the reference's
-  // scalar inner products), then f = (A - s diag(eps^-2, 0))^-1 (-alpha)
   double alpha[4] = {vnf[0], vnf[1], vnf[2], vnf[3] + sdist / dt};
-  const double Yc[3] = {A[3], A[7], A[11]};
-  const double yn = A[15];
-  double beta[3], bb[3];
-  const double a = mu / yn * alpha[3];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    beta[i] = alpha[i] - alpha[3] / yn * Yc[i];
-    bb[i] = mu / yn * Yc[i];
-  }
-  double s = 0.;
-  bool found = false;
-  const bool unit_eps = (eps[0] == 1. && eps[1] == 1. && eps[2] == 1.);
-  if (!(unit_eps && sliding_root_structured(A, alpha, mu, &s, &found))) {
-    const double ycyc = Yc[0] * Yc[0] + Yc[1] * Yc[1] + Yc[2] * Yc[2];
-    const double betab = beta[0] * bb[0] + beta[1] * bb[1] + beta[2] * bb[2];
-    const double betabeta = beta[0] * beta[0] + beta[1] * beta[1] + beta[2] * beta[2];
-    const double bdotb = bb[0] * bb[0] + bb[1] * bb[1] + bb[2] * bb[2];
-    double Bm[36];
-#pragma unroll
-    for (int i = 0; i < 3; ++i)
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        const double e2 = eps[i] * eps[i];
-        const double yhat = A[4 * i + j] - ycyc / yn;
-        Bm[6 * (3 + i) + 3 + j] = e2 * yhat;
-        Bm[6 * i + j] = e2 * (yhat + 2. / a * betab);
-        // dot(E, scalar) is E*scalar in numpy: these two blocks are DIAGONAL
-        Bm[6 * i + 3 + j] = (i == j) ? -(e2 * (betabeta / (a * a))) : 0.;
-        Bm[6 * (3 + i) + j] = (i == j) ? e2 * bdotb - 1. : 0.;
-      }
-    double wr[6], wi[6];
-    if (!eig_real_general6(Bm, wr, wi)) *status |= ARB_STATUS_EIG_NOCONV;
-    found = false;
-    s = 0.;
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-      if (wi[i] == 0. && wr[i] <= 0.) {
-        if (!found || wr[i] < s) s = wr[i];
-        found = true;
-      }
-  }
-  if (!found) { s = -1e10; *status |= ARB_STATUS_EIG_NOROOT; }
-  if (s < -1e10) s = -1e10;
-  double A2[16], nalpha[4], newf[4];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) A2[i] = A[i];
-#pragma unroll
-  for (int i = 0; i < 3; ++i) A2[5 * i] -= s * (1. / (eps[i] * eps[i]));
-#pragma unroll
-  for (int i = 0; i < 4; ++i) nalpha[i] = -alpha[i];
-  if (!solve_small<4>(A2, nalpha, newf)) *status |= ARB_STATUS_SINGULAR;
+  double newf[4];
+  softfinger_sliding(A, alpha, mu, eps, newf, status);
 #pragma unroll
   for (int i = 0; i < 4; ++i) { df[i] = newf[i] - f[i]; f[i] = newf[i]; }
   return 3;

