@@ -186,6 +186,30 @@ ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, 
 // For human36 the sweep order is 4 contacts of the right foot, 4 of the left foot, 2 knee
 // limits (registration order, core.py:929-935): two block switches per sweep instead of a
 // 14x6 update through memory per constraint.
+#ifdef __CUDA_ARCH__
+#define arb_warp_any(pred) (__any_sync(__activemask(), (pred)) != 0)
+#else
+#define arb_warp_any(pred) (pred)
+#endif
+
+// L1 prefetch of one 8-byte element per lane (a 256-byte row per warp); no-op on the host
+ARB_D void arb_prefetch(const double* p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+// operands of the visit of constraint c: T rows, diagonal block, pseudo-inverse, forces
+ARB_D void gs_prefetch_visit(const DevModel& m, const DevBatch& b, int c) {
+  const int r0 = m.crow[c];
+  const double* Tp = ((m.cgen1[c] < 0) ? b.fT0 : b.fT1) + c * (24 * ARB_TILE);
+  const double* pA = b.fAcc + r0 * (4 * ARB_TILE);
+  const double* pP = b.fP + r0 * (4 * ARB_TILE);
+#pragma unroll
+  for (int i = 0; i < 24; ++i) arb_prefetch(Tp + i * ARB_TILE);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { arb_prefetch(pA + i * ARB_TILE); arb_prefetch(pP + i * ARB_TILE); }
+}
+
 struct GsCache {
   int g, n;          // first generator row of the cached block and its size (6 or 1); g < 0: empty
   double u[6], dy[6], L[36];
@@ -557,9 +581,17 @@ ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, doubl
       }
     FT(b.fu, g) = t;
   }
+  // active flags as a bit mask (first 32 constraints; the rest are read from memory)
+  unsigned amask = 0u;
+  for (int c = 0; c < m.nc && c < 32; ++c)
+    if (FT(b.factive, c)) amask |= 1u << c;
   for (int sweep = 0; sweep < ARB_GS_SWEEPS; ++sweep) {
     for (int c = 0; c < m.nc; ++c) {
-      if (!FT(b.factive, c)) continue;
+      const bool act = c < 32 ? ((amask >> c) & 1u) != 0u : FT(b.factive, c) != 0;
+      // Block switches are decided per WARP: every lane still in the loop follows the same
+      // sequence of cached blocks, so the flush/load code runs once per switch, not once per
+      // subset of lanes.  (A lane whose constraint c is inactive just skips the visit.)
+      if (!arb_warp_any(act)) continue;
       const int type = m.ctype[c];
       const int g1 = m.cgen1[c], g0 = m.cgen0[c];
       if (type == ARB_CONS_JOINT_LIMITS) {
@@ -569,6 +601,7 @@ ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, doubl
           gs_cache_flush(m, b, w, k);
           gs_cache_load<true>(m, b, w, k, g1, 1);
         }
+        if (!act) continue;
         const double a = FT(b.fAcc, r0 * 4), p = FT(b.fP, r0 * 4);
         const double f = FT(b.ff, r0), v = k.u[0], q = FT(b.faux, 4 * c);
         const double pred = q + dt * (v - a * f);
@@ -588,7 +621,7 @@ ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, doubl
       }
       if (g1 >= 0 && g0 >= 0) {
         gs_cache_flush(m, b, w, k);
-        gs_visit_two_body(m, b, w, c, dt, &status);
+        if (act) gs_visit_two_body(m, b, w, c, dt, &status);
         continue;
       }
       const int gF = g1 < 0 ? g0 : g1;
@@ -596,6 +629,8 @@ ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, doubl
         gs_cache_flush(m, b, w, k);
         gs_cache_load<true>(m, b, w, k, gF, 6);
       }
+      if (!act) continue;
+      if (c + 1 < m.nc) gs_prefetch_visit(m, b, c + 1);
       if (type == ARB_CONS_BALL_SOCKET) gs_visit_one_body<3>(m, b, w, c, dt, k, &status);
       else gs_visit_one_body<4>(m, b, w, c, dt, k, &status);
     }

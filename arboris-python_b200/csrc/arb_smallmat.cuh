@@ -65,6 +65,9 @@ ARB_D double inv_small_cond(const double* a_in, double* out) {
 }
 
 template <int N>
+ARB_NOINLINE void pinv_jacobi(const double* a, double* out);
+
+template <int N>
 ARB_D void pinv_small(const double* a, double* out) {
   if (N == 1) {
     out[0] = (a[0] != 0.) ? 1. / a[0] : 0.;
@@ -74,6 +77,12 @@ ARB_D void pinv_small(const double* a, double* out) {
   // block with cond_1 < 1e12 loses no singular value and its pseudo-inverse IS its inverse:
   // take the elimination result and leave the SVD to the (near-)singular blocks.
   if (inv_small_cond<N>(a, out) < 1e12) return;
+  pinv_jacobi<N>(a, out);
+}
+
+// one-sided Jacobi SVD (out of line: only (near-)singular blocks get here)
+template <int N>
+ARB_NOINLINE void pinv_jacobi(const double* a, double* out) {
   double U[N * N], V[N * N];
 #pragma unroll
   for (int i = 0; i < N * N; ++i) { U[i] = a[i]; V[i] = ((i % (N + 1)) == 0) ? 1. : 0.; }
@@ -433,6 +442,9 @@ struct PolyRoots<1> {
 //    positive, p > 0 on (x*, inf), so x* is the largest real root.
 // Returns 1 (root in *root), or 0 when the fast path does not apply (complex roots near the
 // path, a multiple root, slow convergence): the caller then isolates the roots rigorously.
+// out-of-line: the rigorous root isolation is the rare path, keep its code out of the hot loop
+ARB_NOINLINE int poly6_roots_slow(const double* p, double T, double* roots) { return PolyRoots<6>::run(p, T, roots); }
+
 #ifdef ARB_HOSTTEST_COUNTERS
 static long arb_fastroot_hits = 0;   // host unit tests only: how often the fast path certified its root
 #endif
@@ -566,7 +578,7 @@ ARB_HD bool sliding_root_structured(const double* A, const double* alpha, double
     if (t < 0.) { *found = false; *s_out = 0.; return true; }   // every real eigenvalue is > 0
   } else {
     double roots[6];
-    const int nr = PolyRoots<6>::run(p, T, roots);
+    const int nr = poly6_roots_slow(p, T, roots);
     if (nr == 0) { *found = false; *s_out = 0.; return true; }
     t = roots[nr - 1];
   }
