@@ -91,6 +91,34 @@ ARB_D void store_se3(double* arr, int j, const Se3& h) {
   for (int i = 0; i < 3; ++i) FT(arr, j * 12 + 9 + i) = h.p[i];
 }
 
+// L1 prefetch of one 8-byte element per lane (a 256-byte row per warp); no-op on the host.
+// The passes below walk the joints in a fixed order and every operand of joint j was written
+// long before (by another pass): asking for the next joint's rows while working on this one
+// hides most of the DRAM / L2 latency that the 8 resident warps per SM cannot.
+ARB_D void arb_prefetch(const double* p) {
+#ifdef __CUDA_ARCH__
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+template <int N>
+ARB_D void arb_prefetch_rows(const double* p) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) arb_prefetch(p + i * ARB_TILE);
+}
+// per-dof rows of joint j in the four arrays a0..a3 (6 rows per dof each)
+ARB_D void artic_prefetch_dofs(const DevModel& m, int j, const double* a0, const double* a1,
+                               const double* a2, const double* a3) {
+  const int nd = arb_joint_ndof(m.jtype[j]);
+  const int off = m.jdof[j] * (6 * ARB_TILE);
+  for (int c = 0; c < nd; ++c) {
+    const int o = off + c * (6 * ARB_TILE);
+    arb_prefetch_rows<6>(a0 + o);
+    arb_prefetch_rows<6>(a1 + o);
+    if (a2) arb_prefetch_rows<6>(a2 + o);
+    if (a3) arb_prefetch_rows<6>(a3 + o);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // root-to-leaf pass: body poses and twists (core.py:1295-1308), theta, X, s, s^
 ARB_D void artic_kinematics(const DevModel& m, const DevBatch& b, int64_t w) {
@@ -197,8 +225,18 @@ ARB_D double artic_tau(const DevModel& m, const DevBatch& b, int64_t w, int k) {
 // reduced right-hand side u of the free motion (w_b = M_b (T_b/dt + gravity_b), tau = PD).
 ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double dt) {
   bool ok = true;
+  // 1/dt once per world: the 36 M_b/dt per body are mostly 0/dt, which sends the fp64 division
+  // through its slow path (a quarter of this stage's instructions before)
+  const double idt = 1. / dt;
   const double gt[6] = {0., 0., 0., m.gravity * m.up[0], m.gravity * m.up[1], m.gravity * m.up[2]};
   for (int j = m.nj - 1; j >= 0; --j) {
+    if (j > 0) {
+      arb_prefetch_rows<6>(b.atw + (j - 1) * (6 * ARB_TILE));
+      arb_prefetch_rows<6>(b.ath + (j - 1) * (6 * ARB_TILE));
+      arb_prefetch_rows<12>(b.aX + (j - 1) * (12 * ARB_TILE));
+      arb_prefetch_rows<12>(b.fpose + (j - 1) * (12 * ARB_TILE));
+      artic_prefetch_dofs(m, j - 1, b.aS, b.aSh, nullptr, nullptr);
+    }
     const int type = m.jtype[j];
     const int par = m.jparent[j];
     const int nd = arb_joint_ndof(type);
@@ -242,11 +280,11 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
         for (int i = 0; i < 3; ++i) { IA[6 * r + i] += c1[i] + c2[i]; IA[6 * r + 3 + i] += c3[i]; }
       }
 #pragma unroll
-      for (int i = 0; i < 36; ++i) { IA[i] += Mb[i] / dt; IM[i] = Mb[i]; }
+      for (int i = 0; i < 36; ++i) { IA[i] += Mb[i] * idt; IM[i] = Mb[i]; }
       // -w_b = -M_b (T/dt + gravity_b)
       double a[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) a[i] = T[i] / dt;
+      for (int i = 0; i < 6; ++i) a[i] = T[i] * idt;
       if ((flags & ARB_BODY_MASSIVE) && m.nweight > 0) {
         Se3 H;
         load_se3(b.fpose, j, H);
@@ -273,11 +311,16 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
 #pragma unroll
       for (int i = 0; i < 36; ++i) IA[i] += Bb[i];
     }
-    if (m.jhaschild[j]) {
+    // children's contributions: every child joint c left X^T IA X, X^T IM X, X^T beta in ITS
+    // OWN slot (no read-modify-write on the way up), summed here
+    for (int c = m.jchild0[j]; c >= 0; c = m.jsib[c]) {
+      const double* pa = b.aIA + c * (36 * ARB_TILE);
+      const double* pm = b.aIM + c * (36 * ARB_TILE);
+      const double* pb = b.abeta + c * (6 * ARB_TILE);
 #pragma unroll
-      for (int i = 0; i < 36; ++i) { IA[i] += FT(b.aIA, j * 36 + i); IM[i] += FT(b.aIM, j * 36 + i); }
+      for (int i = 0; i < 36; ++i) { IA[i] += pa[i * ARB_TILE]; IM[i] += pm[i * ARB_TILE]; }
 #pragma unroll
-      for (int i = 0; i < 6; ++i) beta[i] += FT(b.abeta, j * 6 + i);
+      for (int i = 0; i < 6; ++i) beta[i] += pb[i * ARB_TILE];
     }
     for (int c = nd - 1; c >= 0; --c) {
       const int k = dof + c;
@@ -326,18 +369,13 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
       congruence_up(X, IM);
       double bu[6];
       wrench_up(X, beta, bu);
-      const int pj = par - 1;
-      if (m.jaccfirst[j]) {
+      double* pa = b.aIA + j * (36 * ARB_TILE);
+      double* pm = b.aIM + j * (36 * ARB_TILE);
+      double* pb = b.abeta + j * (6 * ARB_TILE);
 #pragma unroll
-        for (int i = 0; i < 36; ++i) { FT(b.aIA, pj * 36 + i) = IA[i]; FT(b.aIM, pj * 36 + i) = IM[i]; }
+      for (int i = 0; i < 36; ++i) { pa[i * ARB_TILE] = IA[i]; pm[i * ARB_TILE] = IM[i]; }
 #pragma unroll
-        for (int i = 0; i < 6; ++i) FT(b.abeta, pj * 6 + i) = bu[i];
-      } else {
-#pragma unroll
-        for (int i = 0; i < 36; ++i) { FT(b.aIA, pj * 36 + i) += IA[i]; FT(b.aIM, pj * 36 + i) += IM[i]; }
-#pragma unroll
-        for (int i = 0; i < 6; ++i) FT(b.abeta, pj * 6 + i) += bu[i];
-      }
+      for (int i = 0; i < 6; ++i) pb[i * ARB_TILE] = bu[i];
     }
   }
   return ok;
@@ -350,6 +388,10 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
 template <bool MARKED_U>
 ARB_D void artic_forward_full(const DevModel& m, const DevBatch& b, int64_t w, const double* u, double* x) {
   for (int j = 0; j < m.nj; ++j) {
+    if (j + 1 < m.nj) {
+      arb_prefetch_rows<12>(b.aX + (j + 1) * (12 * ARB_TILE));
+      artic_prefetch_dofs(m, j + 1, b.aLA, b.aLM, b.aS, b.aSh);
+    }
     const int par = m.jparent[j];
     const int nd = arb_joint_ndof(m.jtype[j]);
     const int dof = m.jdof[j];
@@ -403,6 +445,12 @@ ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t 
   for (int l = l0; l >= 0; --l) {
     const int k = m.pathdof[off + l];
     const int j = m.dofjoint[k];
+    if (l > 0) {
+      const int kn = m.pathdof[off + l - 1];
+      arb_prefetch_rows<6>(b.aS + kn * (6 * ARB_TILE));
+      arb_prefetch_rows<6>(b.aU + kn * (6 * ARB_TILE));
+      arb_prefetch(b.adinv + kn * ARB_TILE);
+    }
     double s[6], U[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) { s[i] = FT(b.aS, k * 6 + i); U[i] = FT(b.aU, k * 6 + i); }
@@ -437,6 +485,10 @@ ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t 
   const int kc = l0 + 1;   // path dofs 0..l0 carry a non-zero u
   for (int j = 0; j < m.nj; ++j) {
     if (!m.jmark[j]) continue;
+    if (j + 1 < m.nj && m.jmark[j + 1]) {
+      arb_prefetch_rows<12>(b.aX + (j + 1) * (12 * ARB_TILE));
+      artic_prefetch_dofs(m, j + 1, b.aLA, b.aLM, b.aS, b.aSh);
+    }
     const int par = m.jparent[j];
     const int nd = arb_joint_ndof(m.jtype[j]);
     const int dof = m.jdof[j];
@@ -516,10 +568,11 @@ ARB_D void artic_backward_wrenches(const DevModel& m, const DevBatch& b, int64_t
 #pragma unroll
         for (int i = 0; i < 6; ++i) beta[i] -= FT(y, 6 * g + i);
       }
-    if (m.jmarkchild[j]) {
+    for (int c = m.jchild0[j]; c >= 0; c = m.jsib[c])
+      if (m.jmark[c]) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) beta[i] += FT(b.abeta, j * 6 + i);
-    }
+        for (int i = 0; i < 6; ++i) beta[i] += FT(b.abeta, c * 6 + i);
+      }
     for (int c = nd - 1; c >= 0; --c) {
       const int k = dof + c;
       double tau = 0.;
@@ -540,14 +593,8 @@ ARB_D void artic_backward_wrenches(const DevModel& m, const DevBatch& b, int64_t
       load_se3(b.aX, j, X);
       double bu[6];
       wrench_up(X, beta, bu);
-      const int pj = par - 1;
-      if (m.jmarkfirst[j]) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) FT(b.abeta, pj * 6 + i) = bu[i];
-      } else {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) FT(b.abeta, pj * 6 + i) += bu[i];
-      }
+      for (int i = 0; i < 6; ++i) FT(b.abeta, j * 6 + i) = bu[i];
     }
   }
 }

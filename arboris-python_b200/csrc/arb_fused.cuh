@@ -192,12 +192,6 @@ ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, 
 #define arb_warp_any(pred) (pred)
 #endif
 
-// L1 prefetch of one 8-byte element per lane (a 256-byte row per warp); no-op on the host
-ARB_D void arb_prefetch(const double* p) {
-#ifdef __CUDA_ARCH__
-  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#endif
-}
 // operands of the visit of constraint c: T rows, diagonal block, pseudo-inverse, forces
 ARB_D void gs_prefetch_visit(const DevModel& m, const DevBatch& b, int c) {
   const int r0 = m.crow[c];

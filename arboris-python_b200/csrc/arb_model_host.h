@@ -17,6 +17,7 @@ struct HostModel {
   int ngen = 0, ngrows = 0;
   // articulated-body tables
   std::vector<int> dofjoint, jhaschild, jaccfirst, jmark, jmarkfirst, jmarkchild, glimdof, pd_gpos;
+  std::vector<int> jchild0, jsib;   // first child joint of body j+1 / next sibling joint (-1: none), ascending
   std::vector<double> pd_kp, pd_kd, pd_qd, pd_c;
   int has_pd = 0, nweight = 0;
   double gravity = 0.;
@@ -157,6 +158,13 @@ static inline int build_host_model(const arb_model_desc* d, HostModel& m, std::s
   for (int k = 0; k < m.ndof; ++k) m.dofjoint[k] = m.dofbody[k] - 1;
   m.jhaschild.assign(nj, 0); m.jaccfirst.assign(nj, 0);
   m.jmark.assign(nj, 0); m.jmarkfirst.assign(nj, 0); m.jmarkchild.assign(nj, 0);
+  m.jchild0.assign(nj, -1); m.jsib.assign(nj, -1);
+  for (int j = nj - 1; j >= 0; --j) {
+    const int p = m.jparent[j];
+    if (p == 0) continue;
+    m.jsib[j] = m.jchild0[p - 1];
+    m.jchild0[p - 1] = j;
+  }
   {
     std::vector<int> seen(nj + 1, 0);
     for (int j = nj - 1; j >= 0; --j) {

@@ -61,6 +61,7 @@ struct DevModel {
   const int *jmark;                            // [nj] body j+1 lies on the root path of a generator
   const int *jmarkfirst;                       // [nj] highest-numbered MARKED child of its parent body
   const int *jmarkchild;                       // [nj] body j+1 has marked child joints
+  const int *jchild0, *jsib;                   // [nj] first child joint of body j+1 / next sibling joint (-1: none)
   const int *glimdof;                          // [ngrows - 6 ngen] dof of each joint-limit generator row
   // diagonal PD controllers folded per dof: tau = kp (qd - q) + c, Z[k][k] += dt kp + kd
   int has_pd;

@@ -27,6 +27,7 @@ static DevModel view(const HostModel& h) {
   m.gen_body = h.gen_body.data(); m.cgen1 = h.cgen1.data(); m.cgen0 = h.cgen0.data();
   m.dofjoint = h.dofjoint.data(); m.jhaschild = h.jhaschild.data(); m.jaccfirst = h.jaccfirst.data();
   m.jmark = h.jmark.data(); m.jmarkfirst = h.jmarkfirst.data(); m.jmarkchild = h.jmarkchild.data();
+  m.jchild0 = h.jchild0.data(); m.jsib = h.jsib.data();
   m.glimdof = h.glimdof.data(); m.pd_gpos = h.pd_gpos.data(); m.pd_kp = h.pd_kp.data();
   m.pd_kd = h.pd_kd.data(); m.pd_qd = h.pd_qd.data(); m.pd_c = h.pd_c.data();
   m.has_pd = h.has_pd; m.gravity = h.gravity; m.nweight = h.nweight;
