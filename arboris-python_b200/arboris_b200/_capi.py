@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libarboris_b200.so")
+# ARB_B200_LIB selects another build of the same library (A/B runs of kernel variants)
+LIB_PATH = os.environ.get("ARB_B200_LIB") or os.path.join(_HERE, "lib", "libarboris_b200.so")
 
 c_i32p = C.POINTER(C.c_int32)
 c_dblp = C.POINTER(C.c_double)

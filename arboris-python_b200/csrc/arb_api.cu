@@ -167,6 +167,7 @@ extern "C" int arb_batch_set_option(arb_batch* b, const char* name, int value) {
   const std::string s(name);
   if (s == "force_phases") b->force_phases = value;
   else if (s == "prepare_warp") b->prepare_warp = value;
+  else if (s == "gs_coop") b->gs_coop = value;
   else if (s == "time_stages") {
     b->time_stages = value;
     for (int i = 0; i < 4; ++i) b->stage_ms[i] = 0.;

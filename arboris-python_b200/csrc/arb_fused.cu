@@ -22,6 +22,9 @@ struct FusedState {
   } while (0)
 
 #define FUSED_THREADS 64
+#ifndef GS_L_SMEM
+#define GS_L_SMEM 0     /* 1: the cached Lambda_FF block of the per-lane Gauss-Seidel lives in shared memory */
+#endif
 
 __global__ void __launch_bounds__(FUSED_THREADS) k_fused_prepare_lane(DevModel m, DevBatch b, double dt) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -30,8 +33,38 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_fused_prepare_lane(DevModel m
 }
 __global__ void __launch_bounds__(FUSED_THREADS) k_fused_gs(DevModel m, DevBatch b, double dt) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w < b.W) world_fused_gs(m, fused_tile_view(b, w), w, dt);
+#if GS_L_SMEM
+  __shared__ double sL[36 * FUSED_THREADS];
+  if (w < b.W) world_fused_gs(m, fused_tile_view(b, w), w, dt, sL + threadIdx.x, FUSED_THREADS);
+#else
+  double Lr[36];
+  if (w < b.W) world_fused_gs(m, fused_tile_view(b, w), w, dt, Lr, 1);
+#endif
 }
+// block-cooperative Gauss-Seidel: the sliding-friction solves of a visit are pooled over the
+// block through shared memory (world_fused_gs_coop)
+#define GS_COOP_THREADS 128
+#define GS_COOP_CAP 48        /* queue slots: ~0.2 x 128 sliding contacts per visit in steady state, + 4 sigma */
+#ifndef GS_COOP_MINBLOCKS
+#define GS_COOP_MINBLOCKS 3
+#endif
+#define GS_COOP_SMEM (((ARB_SLIDE_NDBL + 4) * GS_COOP_CAP + 1) * sizeof(double) + \
+                      (GS_COOP_CAP + 2) * sizeof(int))
+__global__ void __launch_bounds__(GS_COOP_THREADS, GS_COOP_MINBLOCKS) k_fused_gs_coop(DevModel m, DevBatch b, double dt) {
+  extern __shared__ double smem[];
+  GsCoop co;
+  co.q = smem;                                         // [21][cap]
+  co.r = co.q + ARB_SLIDE_NDBL * GS_COOP_CAP;          // [4][cap]
+  co.bm = (unsigned long long*)(co.r + 4 * GS_COOP_CAP);
+  co.rs = (int*)(co.bm + 1);                           // [cap]
+  co.cnt = co.rs + GS_COOP_CAP;                        // [2]
+  co.cap = GS_COOP_CAP; co.tid = threadIdx.x; co.nthr = GS_COOP_THREADS; co.parity = 0;
+  const int64_t w = (int64_t)blockIdx.x * GS_COOP_THREADS + threadIdx.x;
+  const bool valid = w < b.W;
+  double Lr[36];     // cached Lambda_FF block: registers (shared memory would shrink the L1)
+  world_fused_gs_coop(m, fused_tile_view(b, valid ? w : b.W - 1), w, valid, dt, co, Lr, 1);
+}
+
 __global__ void __launch_bounds__(FUSED_THREADS) k_fused_finish(DevModel m, DevBatch b, double dt) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w < b.W) world_fused_finish(m, fused_tile_view(b, w), w, dt);
@@ -50,6 +83,11 @@ static int ensure_fused_scratch(arb_batch* b) {
   CUDA_OKF(cudaMemsetAsync(f->dbl, 0, sizeof(double) * s.total_doubles() * W, b->stream));
   CUDA_OKF(cudaMemsetAsync(f->ints, 0, sizeof(int) * s.total_ints() * W, b->stream));
   carve_fused(s, f->dbl, f->ints, b->d);
+  CUDA_OKF(cudaFuncSetAttribute(k_fused_gs_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_COOP_SMEM));
+  // the per-lane stages live on L1 (operands re-read every sweep / pass): no shared-memory carve-out
+  CUDA_OKF(cudaFuncSetAttribute(k_fused_gs, cudaFuncAttributePreferredSharedMemoryCarveout, GS_L_SMEM ? 20 : 0));
+  CUDA_OKF(cudaFuncSetAttribute(k_fused_prepare_lane, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
+  CUDA_OKF(cudaFuncSetAttribute(k_fused_finish, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   b->fused = f;
   return 0;
 }
@@ -69,7 +107,13 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
     if (ev[0]) cudaEventRecord(ev[0], b->stream);
     k_fused_prepare_lane<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
     if (ev[0]) cudaEventRecord(ev[1], b->stream);
-    if (b->m.nc > 0) k_fused_gs<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    if (b->m.nc > 0) {
+      if (b->m.nc <= 64 && b->gs_coop)
+        k_fused_gs_coop<<<(unsigned)((b->d.W + GS_COOP_THREADS - 1) / GS_COOP_THREADS), GS_COOP_THREADS,
+                          GS_COOP_SMEM, b->stream>>>(b->m, b->d, dt);
+      else
+        k_fused_gs<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    }
     if (ev[0]) cudaEventRecord(ev[2], b->stream);
     k_fused_finish<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
     b->launches += (b->m.nc > 0) ? 3 : 2;

@@ -206,8 +206,11 @@ ARB_D void gs_prefetch_visit(const DevModel& m, const DevBatch& b, int c) {
 
 struct GsCache {
   int g, n;          // first generator row of the cached block and its size (6 or 1); g < 0: empty
-  double u[6], dy[6], L[36];
+  double u[6], dy[6];
+  double* L;         // Lambda_FF, element i at L[i * ls]: shared memory on the device ([36][threads],
+  int ls;            // conflict-free), a plain array on the host -- 72 registers the visit needs
 };
+#define GSL(k, i) (k).L[(i) * (k).ls]
 
 ARB_D void gs_cache_flush(const DevModel& m, const DevBatch& b, int64_t w, GsCache& k) {
   const int NG = m.ngrows;
@@ -260,22 +263,22 @@ ARB_D void gs_cache_load(const DevModel& m, const DevBatch& b, int64_t w, GsCach
     for (int p = 0; p < 6; ++p) {
       k.u[p] = WITH_U ? pu[p * ARB_TILE] : 0.;
 #pragma unroll
-      for (int q = 0; q < 6; ++q) k.L[6 * p + q] = pl[q * ARB_TILE];
+      for (int q = 0; q < 6; ++q) GSL(k, 6 * p + q) = pl[q * ARB_TILE];
       pl += rowstride;
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < 36; ++i) k.L[i] = 0.;
+    for (int i = 0; i < 36; ++i) GSL(k, i) = 0.;
 #pragma unroll
     for (int p = 0; p < 6; ++p) k.u[p] = 0.;
-    k.L[0] = pl[0];
+    GSL(k, 0) = pl[0];
     if (WITH_U) k.u[0] = pu[0];
   }
 }
 
 // one visit of a constraint that touches TWO generator bodies (e.g. a ball-and-socket joint
 // between two moving bodies): everything through memory.
-ARB_D void gs_visit_two_body(const DevModel& m, const DevBatch& b, int64_t w, int c, double dt, int* status) {
+ARB_NOINLINE void gs_visit_two_body(const DevModel& m, const DevBatch& b, int64_t w, int c, double dt, int* status) {
   const int NG = m.ngrows;
   const int type = m.ctype[c];
   const double* cd = m.cdbl + ARB_CONS_NDBL * c;
@@ -444,7 +447,7 @@ ARB_D void gs_visit_one_body(const DevModel& m, const DevBatch& b, int64_t w, in
   for (int q = 0; q < 6; ++q) {
     double acc = 0.;
 #pragma unroll
-    for (int p = 0; p < 6; ++p) acc += k.L[6 * q + p] * wv[p];
+    for (int p = 0; p < 6; ++p) acc += GSL(k, 6 * q + p) * wv[p];
     k.u[q] += acc;
   }
 }
@@ -464,7 +467,7 @@ ARB_D void gs_diag_one_body(const DevModel& m, const DevBatch& b, int64_t w, int
     for (int q = 0; q < 6; ++q) {
       double acc = 0.;
 #pragma unroll
-      for (int p = 0; p < 6; ++p) acc += T[i * 6 + p] * k.L[6 * p + q];
+      for (int p = 0; p < 6; ++p) acc += T[i * 6 + p] * GSL(k, 6 * p + q);
       tl[q] = acc;
     }
 #pragma unroll
@@ -480,19 +483,16 @@ ARB_D void gs_diag_one_body(const DevModel& m, const DevBatch& b, int64_t w, int
   for (int i = 0; i < ND * ND; ++i) { FT(b.fAcc, r0 * 4 + i) = A[i]; FT(b.fP, r0 * 4 + i) = P[i]; }
 }
 
-ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, double dt) {
+// Start of the Gauss-Seidel of one world: diagonal Delassus blocks and their pseudo-inverses,
+// y0 = sum T_c^T f_c (only ball-and-socket forces persist across steps), u = v0 + Lambda y0.
+ARB_NOINLINE void gs_prologue(const DevModel& m, const DevBatch& b, int64_t w) {
   const int NG = m.ngrows;
-  int status = 0;
-  bool any = false;
-  for (int c = 0; c < m.nc; ++c) any = any || FT(b.factive, c);
-  for (int g = 0; g < NG; ++g) FT(b.fy, g) = 0.;
-  if (!any) return;
-  // constraint forces live in tiled scratch during the sweeps (ball-and-socket rows carry
-  // the warm start, the others were reset by the prepare stage)
-  for (int r = 0; r < m.nrows; ++r) FT(b.ff, r) = ST(b.cforce, r);
-  GsCache k;
+  GsCache k;       // own cache and block storage: nothing of the caller's escapes into this call,
+  double Lp[36];   // so the sweep loop's cache stays in registers
   k.g = -1;
   k.n = 0;
+  k.L = Lp;
+  k.ls = 1;
   // y0 = sum T_c^T f_c (warm start of ball-and-socket forces), diagonal blocks and pinv
   bool warm = false;
   for (int c = 0; c < m.nc; ++c) {
@@ -564,7 +564,6 @@ ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, doubl
       warm = true;
     }
   }
-  k.g = -1;
   // u = v0 + Lambda y0
   for (int g = 0; g < NG; ++g) {
     double t = FT(b.fv0, g);
@@ -575,6 +574,46 @@ ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, doubl
       }
     FT(b.fu, g) = t;
   }
+}
+
+// JointLimits.solve (constraints.py:73-90) on the cached 1-row block
+ARB_D void gs_visit_limit(const DevModel& m, const DevBatch& b, int c, double dt, GsCache& k) {
+  const double* cd = m.cdbl + ARB_CONS_NDBL * c;
+  const int r0 = m.crow[c];
+  const double a = FT(b.fAcc, r0 * 4), p = FT(b.fP, r0 * 4);
+  const double f = FT(b.ff, r0), v = k.u[0], q = FT(b.faux, 4 * c);
+  const double pred = q + dt * (v - a * f);
+  double nf;
+  int br;
+  if (pred <= cd[0]) { nf = p * ((cd[0] - pred) / dt); br = 2; }
+  else if (cd[1] <= pred) { nf = p * ((cd[1] - pred) / dt); br = 3; }
+  else { nf = 0.; br = 1; }
+  const double df = nf - f;
+  FT(b.ff, r0) = nf;
+  FT(b.fbranch, c) = br;
+  if (df != 0.) {
+    k.dy[0] += df;
+    k.u[0] += GSL(k, 0) * df;
+  }
+}
+
+ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, double dt, double* Lstore,
+                          int Lstride) {
+  const int NG = m.ngrows;
+  int status = 0;
+  bool any = false;
+  for (int c = 0; c < m.nc; ++c) any = any || FT(b.factive, c);
+  for (int g = 0; g < NG; ++g) FT(b.fy, g) = 0.;
+  if (!any) return;
+  // constraint forces live in tiled scratch during the sweeps (ball-and-socket rows carry
+  // the warm start, the others were reset by the prepare stage)
+  for (int r = 0; r < m.nrows; ++r) FT(b.ff, r) = ST(b.cforce, r);
+  GsCache k;
+  k.g = -1;
+  k.n = 0;
+  k.L = Lstore;
+  k.ls = Lstride;
+  gs_prologue(m, b, w);
   // active flags as a bit mask (first 32 constraints; the rest are read from memory)
   unsigned amask = 0u;
   for (int c = 0; c < m.nc && c < 32; ++c)
@@ -595,22 +634,7 @@ ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, doubl
           gs_cache_flush(m, b, w, k);
           gs_cache_load<true>(m, b, w, k, g1, 1);
         }
-        if (!act) continue;
-        const double a = FT(b.fAcc, r0 * 4), p = FT(b.fP, r0 * 4);
-        const double f = FT(b.ff, r0), v = k.u[0], q = FT(b.faux, 4 * c);
-        const double pred = q + dt * (v - a * f);
-        double nf;
-        int br;
-        if (pred <= cd[0]) { nf = p * ((cd[0] - pred) / dt); br = 2; }
-        else if (cd[1] <= pred) { nf = p * ((cd[1] - pred) / dt); br = 3; }
-        else { nf = 0.; br = 1; }
-        const double df = nf - f;
-        FT(b.ff, r0) = nf;
-        FT(b.fbranch, c) = br;
-        if (df != 0.) {
-          k.dy[0] += df;
-          k.u[0] += k.L[0] * df;
-        }
+        if (act) gs_visit_limit(m, b, c, dt, k);
         continue;
       }
       if (g1 >= 0 && g0 >= 0) {
@@ -632,6 +656,258 @@ ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, doubl
   gs_cache_flush(m, b, w, k);
   for (int r = 0; r < m.nrows; ++r) ST(b.cforce, r) = FT(b.ff, r);
   if (status) b.status[w] |= status;
+}
+
+// ---------------------------------------------------------------------------------------
+// Gauss-Seidel, block-cooperative form (the one the CUDA kernel runs).
+//
+// Same arithmetic per world as world_fused_gs above, but the worlds of one thread block walk
+// the (sweep, constraint) sequence in lockstep and the SLIDING-friction solves of a visit --
+// needed by ~20 % of the contacts in steady state, ~5x the cost of the rest of the visit, and
+// therefore executed at 3-7 active lanes per warp when each lane solves its own -- are pooled:
+// the lanes that need one push (A, alpha, mu) into a shared-memory queue, the block meets at a
+// barrier, the first n threads solve the n problems with full warps, a second barrier, and the
+// owners pick their forces up.  The order of operations inside each world is unchanged
+// (constraint order of core.py:929-935), so results are bit-identical to the per-lane form.
+#define ARB_SLIDE_NDBL 21      /* A (16), alpha (4), mu */
+struct GsCoop {
+  double* q;                 // [ARB_SLIDE_NDBL][cap] problems, element-major
+  double* r;                 // [4][cap] new forces
+  int* rs;                   // [cap] status bits of each solve
+  int* cnt;                  // [2] problem counters, alternating between visits
+  unsigned long long* bm;    // [1] OR of the active masks of the block's worlds
+  int cap, tid, nthr, parity;
+};
+ARB_D void coop_sync() {
+#ifdef __CUDA_ARCH__
+  __syncthreads();
+#endif
+}
+ARB_D int coop_inc(int* p) {
+#ifdef __CUDA_ARCH__
+  return atomicAdd(p, 1);
+#else
+  return (*p)++;
+#endif
+}
+ARB_D void coop_or(unsigned long long* p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+  if (v) atomicOr(p, v);
+#else
+  *p |= v;
+#endif
+}
+// barrier, the first n threads solve the n queued problems, barrier
+ARB_D void coop_solve_sliding(GsCoop& co, const double* eps) {
+  coop_sync();
+  const int n = co.cnt[co.parity] < co.cap ? co.cnt[co.parity] : co.cap;
+  for (int s = co.tid; s < n; s += co.nthr) {
+    double A[16], alpha[4], newf[4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) A[i] = co.q[i * co.cap + s];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) alpha[i] = co.q[(16 + i) * co.cap + s];
+    const double mu = co.q[20 * co.cap + s];
+    int st = 0;
+    softfinger_sliding(A, alpha, mu, eps, newf, &st);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) co.r[i * co.cap + s] = newf[i];
+    co.rs[s] = st;
+  }
+  if (co.tid == 0) co.cnt[co.parity ^ 1] = 0;
+  coop_sync();
+  co.parity ^= 1;
+}
+
+// soft-finger visit, part 1 (before the pooled solve): returns the branch (1 separating,
+// 2 static, 3 sliding: problem queued in *slot); f is updated for branches 1 and 2
+ARB_D int gs_softfinger_begin(const DevModel& m, const DevBatch& b, int c, double dt, const GsCache& k,
+                              GsCoop& co, double* f, double* df, int* slot, int* status) {
+  const double* cd = m.cdbl + ARB_CONS_NDBL * c;
+  const int r0 = m.crow[c];
+  const bool side0 = m.cgen1[c] < 0;
+  const double* Tp = (side0 ? b.fT0 : b.fT1) + c * (24 * ARB_TILE);
+  const double sign = side0 ? -1. : 1.;
+  const double* pf = b.ff + r0 * ARB_TILE;
+  const double* pA = b.fAcc + r0 * (4 * ARB_TILE);
+  const double* pP = b.fP + r0 * (4 * ARB_TILE);
+  const double sdist = b.faux[c * (4 * ARB_TILE)];
+  const double mu = cd[36];
+  const double* eps = cd + 37;
+  double v[4], vnf[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double acc = 0.;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) acc += Tp[(i * 6 + p) * ARB_TILE] * k.u[p];
+    v[i] = sign * acc;
+    f[i] = pf[i * ARB_TILE];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double t = 0.;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t += pA[(4 * i + j) * ARB_TILE] * f[j];
+    vnf[i] = v[i] - t;
+  }
+  if (sdist + dt * vnf[3] > 0.) {  // separating: release          (constraints.py:781-785)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { df[i] = -f[i]; f[i] = 0.; }
+    return 1;
+  }
+  const double sd_dt = sdist / dt;
+  const double rhs[4] = {v[0], v[1], v[2], v[3] + sd_dt};
+  double nf[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double t = 0.;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t += -pP[(4 * i + j) * ARB_TILE] * rhs[j];
+    df[i] = t;
+    nf[i] = f[i] + t;
+  }
+  double lhs = 0.;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { const double t = nf[i] / eps[i]; lhs += t * t; }
+  const double rr = nf[3] * mu;
+  if (lhs <= rr * rr) {            // static friction holds          (constraints.py:795-802)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = nf[i];
+    return 2;
+  }
+  // sliding: queue (A, alpha, mu)                                  (constraints.py:803-836)
+  const int s = coop_inc(&co.cnt[co.parity]);
+  *slot = s;
+  if (s < co.cap) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) co.q[i * co.cap + s] = pA[i * ARB_TILE];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) co.q[(16 + i) * co.cap + s] = vnf[i];
+    co.q[19 * co.cap + s] = vnf[3] + sd_dt;
+    co.q[20 * co.cap + s] = mu;
+  } else {
+    // queue full (more sliding contacts in this visit than it holds): solve in place
+    double A[16], newf[4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) A[i] = pA[i * ARB_TILE];
+    const double alpha[4] = {vnf[0], vnf[1], vnf[2], vnf[3] + sd_dt};
+    softfinger_sliding(A, alpha, mu, eps, newf, status);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { df[i] = newf[i] - f[i]; f[i] = newf[i]; }
+  }
+  return 3;
+}
+
+// soft-finger visit, part 2: pick up the pooled result, store the force, update the block
+ARB_D void gs_softfinger_end(const DevModel& m, const DevBatch& b, int c, GsCache& k, const GsCoop& co,
+                             int br, int slot, double* f, double* df, int* status) {
+  const int r0 = m.crow[c];
+  const bool side0 = m.cgen1[c] < 0;
+  const double* Tp = (side0 ? b.fT0 : b.fT1) + c * (24 * ARB_TILE);
+  const double sign = side0 ? -1. : 1.;
+  double* pf = b.ff + r0 * ARB_TILE;
+  if (br == 3 && slot < co.cap) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double nf = co.r[i * co.cap + slot];
+      df[i] = nf - f[i];
+      f[i] = nf;
+    }
+    *status |= co.rs[slot];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pf[i * ARB_TILE] = f[i];
+  b.fbranch[c * ARB_TILE] = br;
+  double wv[6];
+#pragma unroll
+  for (int p = 0; p < 6; ++p) {
+    double acc = 0.;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc += Tp[(i * 6 + p) * ARB_TILE] * df[i];
+    wv[p] = sign * acc;
+    k.dy[p] += wv[p];
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    double acc = 0.;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) acc += GSL(k, 6 * q + p) * wv[p];
+    k.u[q] += acc;
+  }
+}
+
+// `valid`: this thread has a world (w < W); threads without one only take part in the barriers.
+// Supports up to 64 constraints (the active set is a bit mask).
+ARB_D void world_fused_gs_coop(const DevModel& m, const DevBatch& b, int64_t w, bool valid, double dt,
+                               GsCoop& co, double* Lstore, int Lstride) {
+  const int NG = m.ngrows;
+  int status = 0;
+  unsigned long long amask = 0ull;
+  if (valid) {
+    for (int c = 0; c < m.nc; ++c)
+      if (FT(b.factive, c)) amask |= 1ull << c;
+    for (int g = 0; g < NG; ++g) FT(b.fy, g) = 0.;
+  }
+  if (co.tid == 0) { *co.bm = 0ull; co.cnt[0] = 0; co.cnt[1] = 0; }
+  coop_sync();
+  coop_or(co.bm, amask);
+  coop_sync();
+  const unsigned long long bm = *co.bm;
+  if (bm == 0ull) return;                    // no world of this block has an active constraint
+  const bool live = amask != 0ull;
+  GsCache k;
+  k.g = -1;
+  k.n = 0;
+  k.L = Lstore;
+  k.ls = Lstride;
+  if (live) {
+    for (int r = 0; r < m.nrows; ++r) FT(b.ff, r) = ST(b.cforce, r);
+    gs_prologue(m, b, w);
+  }
+  k.g = -1;
+  for (int sweep = 0; sweep < ARB_GS_SWEEPS; ++sweep) {
+    for (int c = 0; c < m.nc; ++c) {
+      if (!((bm >> c) & 1ull)) continue;     // block-uniform: everybody walks the same sequence
+      const bool act = ((amask >> c) & 1ull) != 0ull;
+      const int type = m.ctype[c];
+      const int g1 = m.cgen1[c], g0 = m.cgen0[c];
+      if (type == ARB_CONS_JOINT_LIMITS) {
+        if (live && k.g != g1) {
+          gs_cache_flush(m, b, w, k);
+          gs_cache_load<true>(m, b, w, k, g1, 1);
+        }
+        if (act) gs_visit_limit(m, b, c, dt, k);
+        continue;
+      }
+      if (g1 >= 0 && g0 >= 0) {
+        if (live) gs_cache_flush(m, b, w, k);
+        if (act) gs_visit_two_body(m, b, w, c, dt, &status);
+        continue;
+      }
+      const int gF = g1 < 0 ? g0 : g1;
+      if (live && k.g != gF) {
+        gs_cache_flush(m, b, w, k);
+        gs_cache_load<true>(m, b, w, k, gF, 6);
+      }
+      if (type == ARB_CONS_BALL_SOCKET) {
+        if (act) gs_visit_one_body<3>(m, b, w, c, dt, k, &status);
+        continue;
+      }
+      double f[4], df[4];
+      int br = 0, slot = 0;
+      if (act) {
+        if (c + 1 < m.nc) gs_prefetch_visit(m, b, c + 1);
+        br = gs_softfinger_begin(m, b, c, dt, k, co, f, df, &slot, &status);
+      }
+      coop_solve_sliding(co, m.cdbl + ARB_CONS_NDBL * c + 37);
+      if (act) gs_softfinger_end(m, b, c, k, co, br, slot, f, df, &status);
+    }
+  }
+  if (live) {
+    gs_cache_flush(m, b, w, k);
+    for (int r = 0; r < m.nrows; ++r) ST(b.cforce, r) = FT(b.ff, r);
+    if (status) b.status[w] |= status;
+  }
 }
 
 // ---------------------------------------------------------------------------------------

@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.)
+    ap.add_argument("--opt", action="append", help="arb_batch_set_option switch, name=value (A/B runs)")
     return ap.parse_args()
 
 
@@ -201,6 +202,9 @@ def run_ours(a):
     gp = np.tile(gp, (1, reps))[:, :W]
     gv = np.tile(gv, (1, reps))[:, :W]
     bw = BatchedWorld(model, W, device="cuda:%d" % local)
+    for opt in (a.opt or []):                      # kernel A/B switches: --opt gs_coop=1
+        name, val = opt.split("=")
+        bw.set_option(name, int(val))
     gpos0 = torch.as_tensor(gp, device=bw.device)
     gvel0 = torch.as_tensor(gv, device=bw.device)
     ep = Episodes(W, (bw.gpos, bw.gvel, bw.cforce), (gpos0, gvel0, None),

@@ -129,7 +129,8 @@ int arb_batch_create(const arb_model *model, int64_t nworlds, int device, void *
 void arb_batch_destroy(arb_batch *batch);
 int arb_batch_set_stream(arb_batch *batch, void *stream);
 /* tuning/testing switches: "force_phases" (1: arb_step runs the four API phase kernels
- * instead of the fused stages), "time_stages" (1: CUDA events around every fused stage,
+ * instead of the fused stages), "gs_coop" (1: block-cooperative Gauss-Seidel kernel, sliding solves pooled
+ * through shared memory, instead of the per-lane one; bit-identical results), "time_stages" (1: CUDA events around every fused stage,
  * synchronising after every step -- a diagnostic for bench.py, read with arb_batch_stage_ms;
  * setting it clears the accumulators) */
 int arb_batch_set_option(arb_batch *batch, const char *name, int value);

@@ -40,6 +40,7 @@ struct HostBatch {
   DevBatch b;
   std::vector<double> dbl, fdbl;
   std::vector<int> ints, fints, status;
+  int coop = 1;
 };
 
 extern "C" {
@@ -67,6 +68,7 @@ void* ht_create(const arb_model_desc* d, int64_t W, char* errbuf, int errlen) {
   return hb;
 }
 void ht_destroy(void* p) { delete (HostBatch*)p; }
+void ht_set_coop(void* p, int v) { ((HostBatch*)p)->coop = v; }
 void ht_bind(void* p, double* gpos, double* gvel, double* cforce) {
   HostBatch* hb = (HostBatch*)p;
   hb->b.gpos = gpos; hb->b.gvel = gvel; hb->b.cforce = cforce;
@@ -93,7 +95,18 @@ void ht_fused_step(void* p, double dt) {
   for (int64_t w = 0; w < hb->b.W; ++w) {
     const DevBatch t = fused_tile_view(hb->b, w);
     world_fused_prepare(hb->dm, t, w, dt);
-    world_fused_gs(hb->dm, t, w, dt);
+    double Lst[36];
+    if (hb->coop) {       // block-cooperative form with a "block" of one thread
+      double q[ARB_SLIDE_NDBL], r[4];
+      int rs[1], cnt[2];
+      unsigned long long bm;
+      GsCoop co;
+      co.q = q; co.r = r; co.rs = rs; co.cnt = cnt; co.bm = &bm;
+      co.cap = 1; co.tid = 0; co.nthr = 1; co.parity = 0;
+      world_fused_gs_coop(hb->dm, t, w, true, dt, co, Lst, 1);
+    } else {
+      world_fused_gs(hb->dm, t, w, dt, Lst, 1);
+    }
     world_fused_finish(hb->dm, t, w, dt);
   }
 }

@@ -81,6 +81,11 @@ class HostBatch(object):
     def integrate(self, dt):
         self.L.ht_integrate(self.h, dt)
 
+    def set_coop(self, v):
+        """1 (default): block-cooperative Gauss-Seidel form; 0: per-lane form."""
+        self.L.ht_set_coop.argtypes = [C.c_void_p, C.c_int]
+        self.L.ht_set_coop(self.h, int(v))
+
     def fused_step(self, dt):
         self.L.ht_fused_step(self.h, dt)
 

@@ -187,3 +187,25 @@ def test_ragged_batch_sizes_and_errors(torch_cuda):
         bw.matrix("mass", 0, W + 1)
     with pytest.raises(AssertionError):
         bw.update_controllers(0.)
+
+
+def test_cooperative_gauss_seidel_is_bit_identical_to_per_lane(torch_cuda):
+    """The block-cooperative Gauss-Seidel kernel (sliding solves pooled through shared memory)
+    does the same arithmetic in the same order inside every world as the per-lane kernel:
+    states after 120 steps of falling humanoids (contacts in all three branches) are equal
+    bit for bit, for a batch that is not a multiple of the block size."""
+    from arboris_b200 import scenarios
+    from arboris_b200.flatten import flatten
+    model = flatten(scenarios.BUILDERS["human36_contact"]())
+    W = 1000
+    gpos, gvel = scenarios.initial_states(model, "human36_contact", 0, W)
+    out = []
+    for coop in (1, 0):
+        bw = _batch(model, W)
+        bw.set_option("gs_coop", coop)
+        bw.set_state(gpos, gvel)
+        bw.step(1e-3, 120)
+        out.append(bw.get_state())
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+    assert np.abs(out[0][2]).max() > 0        # contact forces are present

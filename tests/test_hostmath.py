@@ -131,13 +131,15 @@ def test_solve4_and_exp():
 @pytest.mark.parametrize("name,tol", [("simplearm", 1e-12), ("human36_free", 1e-10),
                                       ("ball_socket", 1e-12), ("simplearm_limits", 1e-12),
                                       ("snake_loop", 1e-10), ("human36_contact", 1e-10)])
-def test_fused_algorithm_vs_real_reference(name, tol):
+@pytest.mark.parametrize("coop", [1, 0])
+def test_fused_algorithm_vs_real_reference(name, tol, coop):
     """The fused step's algorithm in scalar form (no-fill tree factorisation of Z instead of
     the explicit inverse, Gauss-Seidel in generator space) against the real reference."""
     model, tr = load_golden(name)
     dt = float(tr["dt"])
     W, T = tr["gpos"].shape[:2]
     hb = harness.HostBatch(model, W)
+    hb.set_coop(coop)
     gpos, gvel = tr["gpos_in"].T.copy(), tr["gvel_in"].T.copy()
     cf = np.zeros((max(model.nrows, 1), W))
     flips, worst = 0, {}
