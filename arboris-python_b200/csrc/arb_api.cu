@@ -65,6 +65,8 @@ static int model_to_device(arb_model* mo, int device) {
   rc |= upload(h.dofbody, &m.dofbody, own); rc |= upload(h.dofpos, &m.dofpos, own);
   rc |= upload(h.gen_body, &m.gen_body, own);
   rc |= upload(h.cgen1, &m.cgen1, own);   rc |= upload(h.cgen0, &m.cgen0, own);
+  rc |= upload(h.gen_aligned, &m.gen_aligned, own); rc |= upload(h.gen_c0, &m.gen_c0, own);
+  rc |= upload(h.caligned, &m.caligned, own);
   m.ngen = h.ngen; m.ngrows = h.ngrows;
   rc |= upload(h.dofjoint, &m.dofjoint, own);   rc |= upload(h.jhaschild, &m.jhaschild, own);
   rc |= upload(h.jaccfirst, &m.jaccfirst, own); rc |= upload(h.jmark, &m.jmark, own);

@@ -432,8 +432,11 @@ ARB_D void artic_forward_full(const DevModel& m, const DevBatch& b, int64_t w, c
 // generalized force on dof `kstart`), restricted to the marked joints:
 //  backward along the path (u stored in au[r][k] for the path dofs), then forward over the
 //  marked joints.  (V of each marked body is left in aV[j][r*12 ..], x in ax[r][k].)
+// `rot` (9 doubles, row-major, or nullptr): the unit wrenches are those of the rotated generator
+// basis G' = blockdiag(R, R) G of a contact-aligned body, i.e. wrench r is row r of blockdiag(R, R).
 template <int NR>
-ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t w, int body, int kstart) {
+ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t w, int body, int kstart,
+                                  const double* rot = nullptr) {
   const int n = m.ndof;
   const int off = m.coloff[body];
   double beta[NR][6];
@@ -441,6 +444,12 @@ ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t 
   for (int r = 0; r < NR; ++r)
 #pragma unroll
     for (int i = 0; i < 6; ++i) beta[r][i] = (kstart < 0 && i == r) ? -1. : 0.;
+  if (rot != nullptr && NR == 6) {
+#pragma unroll
+    for (int r = 0; r < NR; ++r)
+#pragma unroll
+      for (int i = 0; i < 6; ++i) beta[r][i] = ((r < 3) == (i < 3)) ? -rot[3 * (r % 3) + (i % 3)] : 0.;
+  }
   const int l0 = (kstart < 0) ? m.kcols[body] - 1 : m.dofpos[kstart];
   for (int l = l0; l >= 0; --l) {
     const int k = m.pathdof[off + l];
@@ -551,6 +560,20 @@ ARB_D double artic_gen_value(const DevModel& m, const DevBatch& b, int64_t w, in
   if (g < 6 * m.ngen) return FT(b.aV, (m.gen_body[g / 6] - 1) * 72 + r * 12 + g % 6);
   return FT(x, r * m.ndof + m.glimdof[g - 6 * m.ngen]);
 }
+// the 6 rows of generator body gi applied to solution r: V of the body, rotated into the
+// contact-aligned frame (rot = R_e, 9 doubles) when the body is aligned
+ARB_D void artic_gen_block(const DevModel& m, const DevBatch& b, int gi, int r, const double* rot, double* out) {
+  double V[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) V[i] = FT(b.aV, (m.gen_body[gi] - 1) * 72 + r * 12 + i);
+  if (rot != nullptr) {
+    m3_mulv(rot, V, out);
+    m3_mulv(rot, V + 3, out + 3);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) out[i] = V[i];
+  }
+}
 
 // ---------------------------------------------------------------------------------------
 // leaf-to-root pass over the marked joints for the Gauss-Seidel result y (wrenches on the
@@ -565,8 +588,20 @@ ARB_D void artic_backward_wrenches(const DevModel& m, const DevBatch& b, int64_t
     double beta[6] = {0., 0., 0., 0., 0., 0.};
     for (int g = 0; g < m.ngen; ++g)
       if (m.gen_body[g] == j + 1) {
+        if (m.gen_aligned[g]) {     // y is in the contact-aligned frame: wrench = blockdiag(R_e, R_e)^T y
+          double Re[9], yy[6], t[6];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) beta[i] -= FT(y, 6 * g + i);
+          for (int i = 0; i < 9; ++i) Re[i] = FT(b.fRe, 9 * g + i);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) yy[i] = FT(y, 6 * g + i);
+          m3t_mulv(Re, yy, t);
+          m3t_mulv(Re, yy + 3, t + 3);
+#pragma unroll
+          for (int i = 0; i < 6; ++i) beta[i] -= t[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) beta[i] -= FT(y, 6 * g + i);
+        }
       }
     for (int c = m.jchild0[j]; c >= 0; c = m.jsib[c])
       if (m.jmark[c]) {

@@ -26,12 +26,18 @@ struct FusedState {
 #define GS_L_SMEM 0     /* 1: the cached Lambda_FF block of the per-lane Gauss-Seidel lives in shared memory */
 #endif
 
-__global__ void __launch_bounds__(FUSED_THREADS) k_fused_prepare_lane(DevModel m, DevBatch b, double dt) {
+#ifndef PREP_MINBLOCKS
+#define PREP_MINBLOCKS 1    /* resident-CTA floor of the prepare kernel: 4 = 255 registers, 6 = 168, 8 = 128 */
+#endif
+#ifndef GS_MINBLOCKS
+#define GS_MINBLOCKS 1
+#endif
+__global__ void __launch_bounds__(FUSED_THREADS, PREP_MINBLOCKS) k_fused_prepare_lane(DevModel m, DevBatch b, double dt) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= b.W) return;
   world_fused_prepare(m, fused_tile_view(b, w), w, dt);
 }
-__global__ void __launch_bounds__(FUSED_THREADS) k_fused_gs(DevModel m, DevBatch b, double dt) {
+__global__ void __launch_bounds__(FUSED_THREADS, GS_MINBLOCKS) k_fused_gs(DevModel m, DevBatch b, double dt) {
   int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 #if GS_L_SMEM
   __shared__ double sL[36 * FUSED_THREADS];

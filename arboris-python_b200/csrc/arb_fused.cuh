@@ -27,7 +27,7 @@ ARB_D DevBatch fused_tile_view(const DevBatch& b, int64_t w) {
   const int64_t tile = w / ARB_TILE, lane = w % ARB_TILE;
   const int64_t od = tile * b.frec * ARB_TILE + lane, oi = tile * b.firec * ARB_TILE + lane;
   t.fq += od; t.fLam += od; t.fv0 += od; t.fT1 += od; t.fT0 += od; t.fu += od; t.fy += od;
-  t.fAcc += od; t.fP += od; t.faux += od; t.fpose += od; t.ff += od;
+  t.fAcc += od; t.fP += od; t.faux += od; t.fpose += od; t.ff += od; t.fRe += od;
   t.aX += od; t.atw += od; t.ath += od; t.aS += od; t.aSh += od; t.aU += od; t.aLA += od;
   t.aLM += od; t.adinv += od; t.aIA += od; t.aIM += od; t.abeta += od; t.au += od; t.ax += od;
   t.aV += od;
@@ -38,9 +38,12 @@ ARB_D DevBatch fused_tile_view(const DevBatch& b, int64_t w) {
 // Per-constraint update from body poses/twists: activation, aux (sdist / pos0 / q) and the
 // maps T1 (from body1's twist) and T0 (from body0's twist) to the constraint rows.
 // Returns the active flag.  pose/twist accessors go through P (12 doubles) and TW (6).
+// `aligned` (contact of a contact-aligned generator body, arb_model_host.h): instead of the 4x6
+// maps only the translation t_c = R_c^T (p_body1 - p_c0) is returned in T1[0..2]; in the frame
+// R_e = R_c^T R_body1 the map is rows 2:6 of Ad([I, t_c])  (H_01 Ad(bpose1^-1) = Ad(H_gc0^-1 pose1)).
 ARB_D bool constraint_update(const DevModel& m, int c, const Se3& P0, const Se3& P1, const double* TW0,
                              const double* TW1, double q, double dt, double* aux, double* T1,
-                             double* T0, int* zidx) {
+                             double* T0, int* zidx, bool aligned = false) {
   const int type = m.ctype[c];
   const double* cd = m.cdbl + ARB_CONS_NDBL * c;
   if (type == ARB_CONS_JOINT_LIMITS) {
@@ -87,6 +90,11 @@ ARB_D bool constraint_update(const DevModel& m, int c, const Se3& P0, const Se3&
     aux[0] = csdist;
     r0 = 2; nr = 4;
     if (!active) return false;
+    if (aligned) {
+      const double d[3] = {P1.p[0] - Hc0.p[0], P1.p[1] - Hc0.p[1], P1.p[2] - Hc0.p[2]};
+      m3t_mulv(Hc0.R, d, T1);
+      return true;
+    }
   }
   // H_01 = inv(pose0 cb0) (pose1 cb1);  T1 = (Ad(H_01) Ad(cb1^-1))[rows], T0 = Ad(cb0^-1)[rows]
   Se3 F0, F1, F0i, H01;
@@ -111,6 +119,31 @@ ARB_D bool constraint_update(const DevModel& m, int c, const Se3& P0, const Se3&
   return true;
 }
 
+// G applied to the NR solutions of the last articulated solve (x = solutions of the joint-limit
+// rows, V of the generator bodies in aV): out[g * stride + col0 + r] for every generator row g.
+template <int NR>
+ARB_D void fused_gen_rows(const DevModel& m, const DevBatch& b, int64_t w, const double* x, double* out,
+                          int stride, int col0) {
+  for (int gj = 0; gj < m.ngen; ++gj) {
+    double Re[9];
+    const bool al = m.gen_aligned[gj] != 0;
+    if (al) {
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Re[i] = FT(b.fRe, 9 * gj + i);
+    }
+#pragma unroll
+    for (int r = 0; r < NR; ++r) {
+      double v[6];
+      artic_gen_block(m, b, gj, r, al ? Re : nullptr, v);
+#pragma unroll
+      for (int i = 0; i < 6; ++i) FT(out, (6 * gj + i) * stride + col0 + r) = v[i];
+    }
+  }
+  for (int g = 6 * m.ngen; g < m.ngrows; ++g)
+#pragma unroll
+    for (int r = 0; r < NR; ++r) FT(out, g * stride + col0 + r) = FT(x, r * m.ndof + m.glimdof[g - 6 * m.ngen]);
+}
+
 // ---------------------------------------------------------------------------------------
 // prepare: see the header.  Reads the bound state only; writes the fused scratch.
 ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, double dt) {
@@ -118,6 +151,21 @@ ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, 
   artic_kinematics(m, b, w);
   if (!artic_factor(m, b, w, dt)) b.status[w] |= ARB_STATUS_SINGULAR;
   artic_forward_full<false>(m, b, w, b.au, b.fq);   // q_free
+  // frames of the contact-aligned generator bodies: R_e = R_c^T R_body
+  for (int gi = 0; gi < m.ngen; ++gi) {
+    if (!m.gen_aligned[gi]) continue;
+    double Rc[9], Rb[9], Re[9];
+    int zi[3];
+    zaligned(m.cdbl + ARB_CONS_NDBL * m.gen_c0[gi] + 32, Rc, zi);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Rb[i] = FT(b.fpose, (m.gen_body[gi] - 1) * 12 + i);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) Re[3 * i + j] = Rc[i] * Rb[j] + Rc[3 + i] * Rb[3 + j] + Rc[6 + i] * Rb[6 + j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) FT(b.fRe, 9 * gi + i) = Re[i];
+  }
   // constraints: activation, T maps
   bool any = false;
   for (int c = 0; c < m.nc; ++c) {
@@ -145,14 +193,20 @@ ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, 
         TW0[i] = (ci[0] == 0) ? 0. : FT(b.atw, (ci[0] - 1) * 6 + i);
         TW1[i] = (ci[1] == 0) ? 0. : FT(b.atw, (ci[1] - 1) * 6 + i);
       }
-      act = constraint_update(m, c, P0, P1, TW0, TW1, 0., dt, aux, T1, T0, zi);
+      const bool aligned = m.caligned[c] != 0;
+      act = constraint_update(m, c, P0, P1, TW0, TW1, 0., dt, aux, T1, T0, zi, aligned);
       if (type == ARB_CONS_SOFT_FINGER_PLANE_POINT) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) ST(b.cforce, r0 + i) = 0.;
       }
       if (act) {
-        const int nr = arb_cons_ndol(type);
-        for (int i = 0; i < nr * 6; ++i) { FT(b.fT1, c * 24 + i) = T1[i]; FT(b.fT0, c * 24 + i) = T0[i]; }
+        if (aligned) {
+#pragma unroll
+          for (int i = 0; i < 3; ++i) FT(b.fT1, c * 24 + i) = T1[i];
+        } else {
+          const int nr = arb_cons_ndol(type);
+          for (int i = 0; i < nr * 6; ++i) { FT(b.fT1, c * 24 + i) = T1[i]; FT(b.fT0, c * 24 + i) = T0[i]; }
+        }
       }
     }
 #pragma unroll
@@ -162,16 +216,23 @@ ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, 
   }
   if (!any) return;
   // generator space: v0 = G q_free, Lambda = G Z^-1 G^T (column block by column block)
-  for (int g = 0; g < NG; ++g) FT(b.fv0, g) = artic_gen_value(m, b, w, g, 0, b.fq);
+  // (rows of a contact-aligned body are taken in its frame R_e: G' = blockdiag(R_e, R_e) G)
+  fused_gen_rows<1>(m, b, w, b.fq, b.fv0, 1, 0);
   for (int gi = 0; gi < m.ngen; ++gi) {
-    artic_solve_generators<6>(m, b, w, m.gen_body[gi], -1);
-    for (int r = 0; r < 6; ++r)
-      for (int g = 0; g < NG; ++g) FT(b.fLam, g * NG + 6 * gi + r) = artic_gen_value(m, b, w, g, r, b.ax);
+    if (m.gen_aligned[gi]) {
+      double Re[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Re[i] = FT(b.fRe, 9 * gi + i);
+      artic_solve_generators<6>(m, b, w, m.gen_body[gi], -1, Re);
+    } else {
+      artic_solve_generators<6>(m, b, w, m.gen_body[gi], -1);
+    }
+    fused_gen_rows<6>(m, b, w, b.ax, b.fLam, NG, 6 * gi);
   }
   for (int h = 6 * m.ngen; h < NG; ++h) {
     const int k = m.glimdof[h - 6 * m.ngen];
     artic_solve_generators<1>(m, b, w, m.dofbody[k], k);
-    for (int g = 0; g < NG; ++g) FT(b.fLam, g * NG + h) = artic_gen_value(m, b, w, g, 0, b.ax);
+    fused_gen_rows<1>(m, b, w, b.ax, b.fLam, NG, h);
   }
 }
 
@@ -198,8 +259,13 @@ ARB_D void gs_prefetch_visit(const DevModel& m, const DevBatch& b, int c) {
   const double* Tp = ((m.cgen1[c] < 0) ? b.fT0 : b.fT1) + c * (24 * ARB_TILE);
   const double* pA = b.fAcc + r0 * (4 * ARB_TILE);
   const double* pP = b.fP + r0 * (4 * ARB_TILE);
+  if (m.caligned[c]) {
 #pragma unroll
-  for (int i = 0; i < 24; ++i) arb_prefetch(Tp + i * ARB_TILE);
+    for (int i = 0; i < 3; ++i) arb_prefetch(Tp + i * ARB_TILE);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 24; ++i) arb_prefetch(Tp + i * ARB_TILE);
+  }
 #pragma unroll
   for (int i = 0; i < 16; ++i) { arb_prefetch(pA + i * ARB_TILE); arb_prefetch(pP + i * ARB_TILE); }
 }
@@ -341,21 +407,51 @@ ARB_NOINLINE void gs_visit_two_body(const DevModel& m, const DevBatch& b, int64_
   }
 }
 
+// Contact-aligned blocks (arb_model_host.h): the cached twist u = [w; v] of the body is expressed
+// in the frame R_e, where contact c is the translation t = (pt[0], pt[TILE], pt[2 TILE]):
+//   rows [w_z, v_x, v_y, v_z] of Ad([I, t]) u  =  [w_z ; v + t x w]
+//   T^T df = [(0, 0, df_0) + df_123 x t ; df_123]
+// 3 operands per visit instead of the 24 of a general 4x6 map (read twice).
+ARB_D void gs_aligned_rows(const double* pt, const double* u, double* v) {
+  const double t0 = pt[0], t1 = pt[ARB_TILE], t2 = pt[2 * ARB_TILE];
+  v[0] = u[2];
+  v[1] = u[3] + (t1 * u[2] - t2 * u[1]);
+  v[2] = u[4] + (t2 * u[0] - t0 * u[2]);
+  v[3] = u[5] + (t0 * u[1] - t1 * u[0]);
+}
+ARB_D void gs_aligned_wrench(const double* pt, const double* df, double* wv) {
+  const double t0 = pt[0], t1 = pt[ARB_TILE], t2 = pt[2 * ARB_TILE];
+  wv[0] = df[2] * t2 - df[3] * t1;
+  wv[1] = df[3] * t0 - df[1] * t2;
+  wv[2] = (df[1] * t1 - df[2] * t0) + df[0];
+  wv[3] = df[1]; wv[4] = df[2]; wv[5] = df[3];
+}
+// the 4x6 map of an aligned contact, materialised (diagonal Delassus block of the prologue)
+ARB_D void gs_aligned_map(const double* pt, double* T) {
+  const double t0 = pt[0], t1 = pt[ARB_TILE], t2 = pt[2 * ARB_TILE];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) T[i] = 0.;
+  T[2] = 1.;
+  T[6 + 1] = -t2;  T[6 + 2] = t1;   T[6 + 3] = 1.;
+  T[12 + 0] = t2;  T[12 + 2] = -t0; T[12 + 4] = 1.;
+  T[18 + 0] = -t1; T[18 + 1] = t0;  T[18 + 5] = 1.;
+}
+
 // SoftFingerContact.solve (constraints.py:780-836) on tiled operands: pA / pP point at the 4x4
 // diagonal Delassus block and its pseudo-inverse (element i at [i TILE]); they are read where
 // they are used so that neither stays in registers across the sliding solve.
 ARB_D int softfinger_solve_tiled(const double* v, const double* pA, const double* pP, double sdist,
                                  double mu, const double* eps, double dt, double* f, double* df,
                                  int* status) {
-  double vnf[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
+  // (only the normal row of A is needed unless the contact slides)
+  double vnf3;
+  {
     double t = 0.;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) t += pA[(4 * i + j) * ARB_TILE] * f[j];
-    vnf[i] = v[i] - t;
+    for (int j = 0; j < 4; ++j) t += pA[(12 + j) * ARB_TILE] * f[j];
+    vnf3 = v[3] - t;
   }
-  if (sdist + dt * vnf[3] > 0.) {  // separating: release
+  if (sdist + dt * vnf3 > 0.) {  // separating: release
 #pragma unroll
     for (int i = 0; i < 4; ++i) { df[i] = -f[i]; f[i] = 0.; }
     return 1;
@@ -381,10 +477,22 @@ ARB_D int softfinger_solve_tiled(const double* v, const double* pA, const double
     return 2;
   }
   // sliding (only some lanes of the warp get here)
-  double A[16];
+#ifdef ARB_X_NOSLIDE   /* timing experiment only (wrong results): what the sliding solves cost */
+#pragma unroll
+  for (int i = 0; i < 4; ++i) f[i] = nf[i];
+  return 3;
+#endif
+  double A[16], alpha[4];
 #pragma unroll
   for (int i = 0; i < 16; ++i) A[i] = pA[i * ARB_TILE];
-  const double alpha[4] = {vnf[0], vnf[1], vnf[2], vnf[3] + sd_dt};
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double t = 0.;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t += A[4 * i + j] * f[j];
+    alpha[i] = v[i] - t;
+  }
+  alpha[3] = vnf3 + sd_dt;
   double newf[4];
   softfinger_sliding(A, alpha, mu, eps, newf, status);
 #pragma unroll
@@ -405,14 +513,21 @@ ARB_D void gs_visit_one_body(const DevModel& m, const DevBatch& b, int64_t w, in
   const double sign = side0 ? -1. : 1.;
   double* pf = b.ff + r0 * ARB_TILE;
   const double* paux = b.faux + c * (4 * ARB_TILE);
-  double v[ND], f[ND], df[ND];
+  const bool al = ND == 4 && m.caligned[c] != 0;
+  double v[4], f[ND], df[4];
+  if (al) {
+    gs_aligned_rows(Tp, k.u, v);
 #pragma unroll
-  for (int i = 0; i < ND; ++i) {
-    double acc = 0.;
+    for (int i = 0; i < ND; ++i) f[i] = pf[i * ARB_TILE];
+  } else {
 #pragma unroll
-    for (int p = 0; p < 6; ++p) acc += Tp[(i * 6 + p) * ARB_TILE] * k.u[p];
-    v[i] = sign * acc;
-    f[i] = pf[i * ARB_TILE];
+    for (int i = 0; i < ND; ++i) {
+      double acc = 0.;
+#pragma unroll
+      for (int p = 0; p < 6; ++p) acc += Tp[(i * 6 + p) * ARB_TILE] * k.u[p];
+      v[i] = sign * acc;
+      f[i] = pf[i * ARB_TILE];
+    }
   }
   if (ND == 3) {
     const double* pP = b.fP + r0 * (4 * ARB_TILE);
@@ -435,13 +550,19 @@ ARB_D void gs_visit_one_body(const DevModel& m, const DevBatch& b, int64_t w, in
     b.fbranch[c * ARB_TILE] = br;
   }
   double wv[6];
+  if (al) {
+    gs_aligned_wrench(Tp, df, wv);
 #pragma unroll
-  for (int p = 0; p < 6; ++p) {
-    double acc = 0.;
+    for (int p = 0; p < 6; ++p) k.dy[p] += wv[p];
+  } else {
 #pragma unroll
-    for (int i = 0; i < ND; ++i) acc += Tp[(i * 6 + p) * ARB_TILE] * df[i];
-    wv[p] = sign * acc;
-    k.dy[p] += wv[p];
+    for (int p = 0; p < 6; ++p) {
+      double acc = 0.;
+#pragma unroll
+      for (int i = 0; i < ND; ++i) acc += Tp[(i * 6 + p) * ARB_TILE] * df[i];
+      wv[p] = sign * acc;
+      k.dy[p] += wv[p];
+    }
   }
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
@@ -457,9 +578,13 @@ template <int ND>
 ARB_D void gs_diag_one_body(const DevModel& m, const DevBatch& b, int64_t w, int c, const GsCache& k) {
   const int r0 = m.crow[c];
   const double* Tp = ((m.cgen1[c] < 0) ? b.fT0 : b.fT1) + c * (24 * ARB_TILE);
-  double T[ND * 6], A[ND * ND], P[ND * ND];
+  double T[24], A[ND * ND], P[ND * ND];
+  if (ND == 4 && m.caligned[c]) {
+    gs_aligned_map(Tp, T);
+  } else {
 #pragma unroll
-  for (int i = 0; i < ND * 6; ++i) T[i] = Tp[i * ARB_TILE];
+    for (int i = 0; i < ND * 6; ++i) T[i] = Tp[i * ARB_TILE];
+  }
 #pragma unroll
   for (int i = 0; i < ND; ++i) {
     double tl[6];
@@ -618,7 +743,10 @@ ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, doubl
   unsigned amask = 0u;
   for (int c = 0; c < m.nc && c < 32; ++c)
     if (FT(b.factive, c)) amask |= 1u << c;
-  for (int sweep = 0; sweep < ARB_GS_SWEEPS; ++sweep) {
+#ifndef ARB_X_SWEEPS
+#define ARB_X_SWEEPS ARB_GS_SWEEPS   /* timing experiments only */
+#endif
+  for (int sweep = 0; sweep < ARB_X_SWEEPS; ++sweep) {
     for (int c = 0; c < m.nc; ++c) {
       const bool act = c < 32 ? ((amask >> c) & 1u) != 0u : FT(b.factive, c) != 0;
       // Block switches are decided per WARP: every lane still in the loop follows the same
@@ -735,13 +863,19 @@ ARB_D int gs_softfinger_begin(const DevModel& m, const DevBatch& b, int c, doubl
   const double mu = cd[36];
   const double* eps = cd + 37;
   double v[4], vnf[4];
+  if (m.caligned[c]) {
+    gs_aligned_rows(Tp, k.u, v);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    double acc = 0.;
+    for (int i = 0; i < 4; ++i) f[i] = pf[i * ARB_TILE];
+  } else {
 #pragma unroll
-    for (int p = 0; p < 6; ++p) acc += Tp[(i * 6 + p) * ARB_TILE] * k.u[p];
-    v[i] = sign * acc;
-    f[i] = pf[i * ARB_TILE];
+    for (int i = 0; i < 4; ++i) {
+      double acc = 0.;
+#pragma unroll
+      for (int p = 0; p < 6; ++p) acc += Tp[(i * 6 + p) * ARB_TILE] * k.u[p];
+      v[i] = sign * acc;
+      f[i] = pf[i * ARB_TILE];
+    }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -819,13 +953,19 @@ ARB_D void gs_softfinger_end(const DevModel& m, const DevBatch& b, int c, GsCach
   for (int i = 0; i < 4; ++i) pf[i * ARB_TILE] = f[i];
   b.fbranch[c * ARB_TILE] = br;
   double wv[6];
+  if (m.caligned[c]) {
+    gs_aligned_wrench(Tp, df, wv);
 #pragma unroll
-  for (int p = 0; p < 6; ++p) {
-    double acc = 0.;
+    for (int p = 0; p < 6; ++p) k.dy[p] += wv[p];
+  } else {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc += Tp[(i * 6 + p) * ARB_TILE] * df[i];
-    wv[p] = sign * acc;
-    k.dy[p] += wv[p];
+    for (int p = 0; p < 6; ++p) {
+      double acc = 0.;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc += Tp[(i * 6 + p) * ARB_TILE] * df[i];
+      wv[p] = sign * acc;
+      k.dy[p] += wv[p];
+    }
   }
 #pragma unroll
   for (int q = 0; q < 6; ++q) {

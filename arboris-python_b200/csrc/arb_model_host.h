@@ -14,6 +14,7 @@ struct HostModel {
   std::vector<int> jtype, jparent, jdof, jgpos, hcn_ident, bflags, coloff, kcols, pathdof;
   std::vector<int> ctype, cint, crow, atype, aint;
   std::vector<int> dofbody, dofpos, gen_body, cgen1, cgen0;
+  std::vector<int> gen_aligned, gen_c0, caligned;   // contact-aligned generator blocks (arb_fused.cuh)
   int ngen = 0, ngrows = 0;
   // articulated-body tables
   std::vector<int> dofjoint, jhaschild, jaccfirst, jmark, jmarkfirst, jmarkchild, glimdof, pd_gpos;
@@ -148,6 +149,33 @@ static inline int build_host_model(const arb_model_desc* d, HostModel& m, std::s
   }
   m.ngen = (int)m.gen_body.size();
   m.ngrows = 6 * m.ngen;
+  // A generator body is "contact-aligned" when every constraint attached to it is a plane/point
+  // soft-finger contact whose plane is carried by the ground and all those planes share one
+  // normal: the contact frames of the body then share one orientation R_c (zaligned(normal),
+  // collisions.py:200-204), and the Gauss-Seidel keeps the body's rows in the frame
+  // R_e = R_c^T R_body, where each contact is a pure translation t_c (3 numbers instead of a
+  // 4x6 map).  See "contact-aligned blocks" in arb_fused.cuh.
+  m.gen_aligned.assign(m.ngen > 0 ? m.ngen : 1, 0);
+  m.gen_c0.assign(m.ngen > 0 ? m.ngen : 1, -1);
+  m.caligned.assign(m.nc > 0 ? m.nc : 1, 0);
+  for (int g = 0; g < m.ngen; ++g) {
+    bool ok = true;
+    int first = -1;
+    for (int c = 0; c < m.nc && ok; ++c) {
+      if (m.ctype[c] == ARB_CONS_JOINT_LIMITS) continue;
+      if (m.cgen1[c] != 6 * g && m.cgen0[c] != 6 * g) continue;
+      if (m.ctype[c] != ARB_CONS_SOFT_FINGER_PLANE_POINT || m.cgen1[c] != 6 * g || m.cgen0[c] >= 0) { ok = false; break; }
+      if (first < 0) first = c;
+      for (int i = 0; i < 3; ++i)
+        if (m.cdbl[ARB_CONS_NDBL * c + 32 + i] != m.cdbl[ARB_CONS_NDBL * first + 32 + i]) ok = false;
+    }
+    if (ok && first >= 0) {
+      m.gen_aligned[g] = 1;
+      m.gen_c0[g] = first;
+      for (int c = 0; c < m.nc; ++c)
+        if (m.ctype[c] != ARB_CONS_JOINT_LIMITS && m.cgen1[c] == 6 * g) m.caligned[c] = 1;
+    }
+  }
   for (int c = 0; c < m.nc; ++c)
     if (m.ctype[c] == ARB_CONS_JOINT_LIMITS) {
       m.cgen1[c] = m.ngrows++;
@@ -237,10 +265,10 @@ static inline ScratchSizes scratch_sizes(const HostModel& m) {
   return s;
 }
 struct FusedSizes {
-  int64_t fq, fLam, fv0, fT1, fT0, fu, fy, fAcc, fP, faux, fpose, ff, factive, fbranch;
+  int64_t fq, fLam, fv0, fT1, fT0, fu, fy, fAcc, fP, faux, fpose, ff, fRe, factive, fbranch;
   int64_t aX, atw, ath, aS, aSh, aU, aLA, aLM, adinv, aIA, aIM, abeta, au, ax, aV;
   int64_t total_doubles() const {
-    return fq + fLam + fv0 + fT1 + fT0 + fu + fy + fAcc + fP + faux + fpose + ff +
+    return fq + fLam + fv0 + fT1 + fT0 + fu + fy + fAcc + fP + faux + fpose + ff + fRe +
            aX + atw + ath + aS + aSh + aU + aLA + aLM + adinv + aIA + aIM + abeta + au + ax + aV;
   }
   int64_t total_ints() const { return factive + fbranch; }
@@ -252,6 +280,7 @@ static inline FusedSizes fused_sizes(const HostModel& m) {
   const int64_t nj = m.nj > 0 ? m.nj : 1, nn = n > 0 ? n : 1;
   s.fq = nn; s.fLam = NG * NG; s.fv0 = NG; s.fT1 = nc * 24; s.fT0 = nc * 24;
   s.fu = NG; s.fy = NG; s.fAcc = nr * 4; s.fP = nr * 4; s.faux = nc * 4; s.fpose = nj * 12; s.ff = nr;
+  s.fRe = 9 * (m.ngen > 0 ? m.ngen : 1);
   s.factive = nc; s.fbranch = nc;
   s.aX = nj * 12; s.atw = nj * 6; s.ath = nj * 6;
   s.aS = s.aSh = s.aU = s.aLA = s.aLM = nn * 6; s.adinv = nn;
@@ -268,7 +297,7 @@ static inline void carve_fused(const FusedSizes& s, double* dbl, int* ints, DevB
   b.fq = take(s.fq); b.fLam = take(s.fLam); b.fv0 = take(s.fv0);
   b.fT1 = take(s.fT1); b.fT0 = take(s.fT0); b.fu = take(s.fu); b.fy = take(s.fy);
   b.fAcc = take(s.fAcc); b.fP = take(s.fP); b.faux = take(s.faux); b.fpose = take(s.fpose);
-  b.ff = take(s.ff);
+  b.ff = take(s.ff); b.fRe = take(s.fRe);
   b.aX = take(s.aX); b.atw = take(s.atw); b.ath = take(s.ath);
   b.aS = take(s.aS); b.aSh = take(s.aSh); b.aU = take(s.aU); b.aLA = take(s.aLA); b.aLM = take(s.aLM);
   b.adinv = take(s.adinv); b.aIA = take(s.aIA); b.aIM = take(s.aIM); b.abeta = take(s.abeta);

@@ -54,6 +54,9 @@ struct DevModel {
   int ngen, ngrows;                            // generator bodies, total rows NG
   const int *gen_body;                         // [ngen]
   const int *cgen1, *cgen0;                    // [nc] first generator row of body1 / body0 (or -1)
+  const int *gen_aligned;                      // [ngen] rows kept in the contact-aligned frame (arb_model_host.h)
+  const int *gen_c0;                           // [ngen] first contact of an aligned generator (its plane normal)
+  const int *caligned;                         // [nc] contact of an aligned generator: T is a translation
   // ---- articulated-body tables (arb_artic.cuh) -----------------------------------------
   const int *dofjoint;                         // [ndof] joint of each dof
   const int *jhaschild;                        // [nj] body j+1 has child joints
@@ -105,6 +108,7 @@ struct DevBatch {
   double *faux;      // [nc][4]
   double *fpose;     // [nj][12]   body poses (for contacts and gravity)
   double *ff;        // [nrows]    constraint forces during the sweeps
+  double *fRe;       // [ngen][9]  R_e = R_c^T R_body of the contact-aligned generator bodies
   int *factive, *fbranch;  // [nc]
   int64_t frec, firec;     // doubles / ints per world in the tiled fused scratch
   // ---- articulated-body factorisation of Z (arb_artic.cuh), [elem][W] ------------------

@@ -25,6 +25,7 @@ static DevModel view(const HostModel& h) {
   for (int i = 0; i < 3; ++i) m.up[i] = h.up[i];
   m.dofbody = h.dofbody.data(); m.dofpos = h.dofpos.data(); m.ngen = h.ngen; m.ngrows = h.ngrows;
   m.gen_body = h.gen_body.data(); m.cgen1 = h.cgen1.data(); m.cgen0 = h.cgen0.data();
+  m.gen_aligned = h.gen_aligned.data(); m.gen_c0 = h.gen_c0.data(); m.caligned = h.caligned.data();
   m.dofjoint = h.dofjoint.data(); m.jhaschild = h.jhaschild.data(); m.jaccfirst = h.jaccfirst.data();
   m.jmark = h.jmark.data(); m.jmarkfirst = h.jmarkfirst.data(); m.jmarkchild = h.jmarkchild.data();
   m.jchild0 = h.jchild0.data(); m.jsib = h.jsib.data();
@@ -159,6 +160,13 @@ int ht_sliding_root(const double* A, const double* alpha, double mu, double* s, 
   return ok ? 1 : 0;
 }
 long ht_fastroot_hits() { return arb_fastroot_hits; }
+// number of generator bodies; flags[g] = 1 for contact-aligned ones, caligned[c] per constraint
+int ht_aligned(void* p, int* flags, int* caligned) {
+  HostBatch* hb = (HostBatch*)p;
+  for (int g = 0; g < hb->hm.ngen; ++g) flags[g] = hb->hm.gen_aligned[g];
+  for (int c = 0; c < hb->hm.nc; ++c) caligned[c] = hb->hm.caligned[c];
+  return hb->hm.ngen;
+}
 int ht_solve4(const double* a, const double* b, double* x) { return solve_small<4>(a, b, x) ? 1 : 0; }
 void ht_exp(const double* tw, double* out12) {
   Se3 h;

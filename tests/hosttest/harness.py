@@ -69,6 +69,14 @@ class HostBatch(object):
             self.L.ht_destroy(self.h)
             self.h = None
 
+    def aligned(self):
+        """(flags of the generator bodies, flags of the constraints): contact-aligned blocks."""
+        g = np.zeros(64, np.int32)
+        c = np.zeros(max(len(self.model.cons_type), 1), np.int32)
+        self.L.ht_aligned.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        n = self.L.ht_aligned(self.h, g.ctypes.data, c.ctypes.data)
+        return g[:n].copy(), c[:len(self.model.cons_type)].copy()
+
     def update_dynamic(self):
         self.L.ht_update_dynamic(self.h)
 

@@ -210,3 +210,17 @@ def test_structured_sliding_root_vs_numpy_eigvals():
             assert found.value, (trial, ref)
             assert abs(s.value - ref) <= 1e-9*abs(ref) + 1e-13*np.abs(A).max(), (trial, s.value, ref)
     assert nfound > 500 and nnone > 10
+
+
+def test_contact_aligned_blocks_are_detected():
+    """human36 on the ground plane: both feet are contact-aligned generator bodies (their 8
+    plane/point contacts become translations in the Gauss-Seidel); bodies that carry a
+    ball-and-socket constraint are not."""
+    model, _ = load_golden("human36_contact")
+    g, c = harness.HostBatch(model, 1).aligned()
+    assert g.tolist() == [1, 1]
+    assert c.tolist() == [1]*8 + [0, 0]
+    for name in ("snake_loop", "ball_socket"):
+        model, _ = load_golden(name)
+        g, c = harness.HostBatch(model, 1).aligned()
+        assert not g.any() and not c.any()
