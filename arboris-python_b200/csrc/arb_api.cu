@@ -249,6 +249,7 @@ extern "C" int arb_update_constraints(arb_batch* b, double dt) {
   rc = arb_ensure_phase_scratch(b); if (rc) return rc;
   k_update_constraints<<<lpw_grid(b->d.W), LPW_THREADS, 0, b->stream>>>(b->m, b->d, dt);
   LAUNCH_CHECK(b);
+  b->last_fused = 0;
   return 0;
 }
 extern "C" int arb_integrate(arb_batch* b, double dt) {
@@ -276,6 +277,7 @@ int arb_step_phases(arb_batch* b, const double* dts, int nsteps) {
     b->launches += 3;
     LAUNCH_CHECK(b);
   }
+  if (nsteps > 0) b->last_fused = 0;
   return 0;
 }
 
@@ -284,7 +286,9 @@ extern "C" int arb_step(arb_batch* b, const double* dts, int nsteps) {
   if (nsteps < 0 || (nsteps > 0 && !dts)) { arb_set_error("bad dts/nsteps"); return -3; }
   CUDA_OK(cudaSetDevice(b->device));
   if (b->force_phases || !arb_fused_supported(b)) return arb_step_phases(b, dts, nsteps);
-  return arb_fused_step(b, dts, nsteps);
+  rc = arb_fused_step(b, dts, nsteps);
+  if (rc == 0 && nsteps > 0) b->last_fused = 1;
+  return rc;
 }
 
 extern "C" int arb_step_host(arb_batch* b, double* h_gpos, double* h_gvel, double* h_cforce,
@@ -326,6 +330,18 @@ __global__ void k_gather_int(const int* __restrict__ src, int* __restrict__ out,
   int64_t w = i / cnt;
   int e = (int)(i - w * cnt);
   out[i] = src[(int64_t)e * W + w0 + w];
+}
+// the same from the fused scratch, tiled [W/32][record][32]; `first`/`stride` select elements
+// first, first + stride, ... of the array that starts `off` elements into the record
+template <class T>
+__global__ void k_gather_tiled(const T* __restrict__ src, T* __restrict__ out, int cnt, int stride,
+                               int64_t rec, int64_t w0, int64_t nw) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nw * cnt) return;
+  int64_t w = i / cnt;
+  int e = (int)(i - w * cnt);
+  const int64_t ww = w0 + w;
+  out[i] = src[(ww / ARB_TILE) * rec * ARB_TILE + (int64_t)e * stride * ARB_TILE + ww % ARB_TILE];
 }
 __global__ void k_get_body(DevModel m, DevBatch b, int which, int body, double* out, int64_t w0, int64_t nw) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -378,9 +394,10 @@ __global__ void k_get_body(DevModel m, DevBatch b, int which, int body, double* 
   }
 }
 
-static int check_range(arb_batch* b, const void* out, int64_t w0, int64_t w1) {
+static int check_range(arb_batch* b, const void* out, int64_t w0, int64_t w1, bool fused_ok = false) {
   if (!b || !out) { arb_set_error("null argument"); return -1; }
   if (w0 < 0 || w1 > b->d.W || w0 >= w1) { arb_set_error("world range out of bounds"); return -1; }
+  if (fused_ok && b->last_fused) return 0;
   if (!b->scratch_dbl) { arb_set_error("nothing to read: no phase call was made on this batch yet"); return -2; }
   return 0;
 }
@@ -421,11 +438,26 @@ extern "C" int arb_get_body(arb_batch* b, int which, int body, double* out, int6
   return 0;
 }
 extern "C" int arb_get_constraint(arb_batch* b, int which, void* out, int64_t w0, int64_t w1) {
-  int rc = check_range(b, out, w0, w1); if (rc) return rc;
+  int rc = check_range(b, out, w0, w1, true); if (rc) return rc;
   CUDA_OK(cudaSetDevice(b->device));
   const int nc = b->m.nc;
   if (nc == 0) return 0;
   const int64_t nw = w1 - w0;
+  if (b->last_fused) {      // last step ran fused: the quantities live in the tiled fused scratch
+    const int cnt = which == ARB_CONS_ZIDX ? 3 * nc : nc;
+    const unsigned g = (unsigned)((nw * cnt + 255) / 256);
+    if (which == ARB_CONS_SDIST)
+      k_gather_tiled<double><<<g, 256, 0, b->stream>>>(b->d.faux, (double*)out, nc, 4, b->d.frec, w0, nw);
+    else if (which == ARB_CONS_ACTIVE)
+      k_gather_tiled<int><<<g, 256, 0, b->stream>>>(b->d.factive, (int*)out, nc, 1, b->d.firec, w0, nw);
+    else if (which == ARB_CONS_BRANCH)
+      k_gather_tiled<int><<<g, 256, 0, b->stream>>>(b->d.fbranch, (int*)out, nc, 1, b->d.firec, w0, nw);
+    else if (which == ARB_CONS_ZIDX)
+      k_gather_tiled<int><<<g, 256, 0, b->stream>>>(b->d.fzidx, (int*)out, cnt, 1, b->d.firec, w0, nw);
+    else { arb_set_error("unknown constraint quantity"); return -1; }
+    LAUNCH_CHECK(b);
+    return 0;
+  }
   if (which == ARB_CONS_SDIST) {
     // caux is [nc][4]: gather element 4c
     std::vector<double> dummy;

@@ -31,7 +31,7 @@ ARB_D DevBatch fused_tile_view(const DevBatch& b, int64_t w) {
   t.aX += od; t.atw += od; t.ath += od; t.aS += od; t.aSh += od; t.aU += od; t.aLA += od;
   t.aLM += od; t.adinv += od; t.aIA += od; t.aIM += od; t.abeta += od; t.au += od; t.ax += od;
   t.aV += od;
-  t.factive += oi; t.fbranch += oi;
+  t.factive += oi; t.fbranch += oi; t.fzidx += oi;
   return t;
 }
 
@@ -198,6 +198,8 @@ ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, 
       if (type == ARB_CONS_SOFT_FINGER_PLANE_POINT) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) ST(b.cforce, r0 + i) = 0.;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) FT(b.fzidx, 3 * c + i) = zi[i];
       }
       if (act) {
         if (aligned) {

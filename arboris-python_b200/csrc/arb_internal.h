@@ -32,6 +32,7 @@ struct arb_batch {
   int time_stages = 0;             // 1: CUDA events around every fused stage (diagnostic, synchronises per step)
   double stage_ms[4] = {0., 0., 0., 0.};   // accumulated prepare / gs / finish milliseconds, [3] = steps timed
   FusedState* fused = nullptr;
+  int last_fused = 0;              // 1: the constraint read-backs come from the fused scratch (last step was fused)
 };
 
 const char* arb_set_error(const std::string& s);

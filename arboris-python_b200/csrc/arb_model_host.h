@@ -265,13 +265,13 @@ static inline ScratchSizes scratch_sizes(const HostModel& m) {
   return s;
 }
 struct FusedSizes {
-  int64_t fq, fLam, fv0, fT1, fT0, fu, fy, fAcc, fP, faux, fpose, ff, fRe, factive, fbranch;
+  int64_t fq, fLam, fv0, fT1, fT0, fu, fy, fAcc, fP, faux, fpose, ff, fRe, factive, fbranch, fzidx;
   int64_t aX, atw, ath, aS, aSh, aU, aLA, aLM, adinv, aIA, aIM, abeta, au, ax, aV;
   int64_t total_doubles() const {
     return fq + fLam + fv0 + fT1 + fT0 + fu + fy + fAcc + fP + faux + fpose + ff + fRe +
            aX + atw + ath + aS + aSh + aU + aLA + aLM + adinv + aIA + aIM + abeta + au + ax + aV;
   }
-  int64_t total_ints() const { return factive + fbranch; }
+  int64_t total_ints() const { return factive + fbranch + fzidx; }
 };
 static inline FusedSizes fused_sizes(const HostModel& m) {
   FusedSizes s;
@@ -281,7 +281,7 @@ static inline FusedSizes fused_sizes(const HostModel& m) {
   s.fq = nn; s.fLam = NG * NG; s.fv0 = NG; s.fT1 = nc * 24; s.fT0 = nc * 24;
   s.fu = NG; s.fy = NG; s.fAcc = nr * 4; s.fP = nr * 4; s.faux = nc * 4; s.fpose = nj * 12; s.ff = nr;
   s.fRe = 9 * (m.ngen > 0 ? m.ngen : 1);
-  s.factive = nc; s.fbranch = nc;
+  s.factive = nc; s.fbranch = nc; s.fzidx = 3 * nc;
   s.aX = nj * 12; s.atw = nj * 6; s.ath = nj * 6;
   s.aS = s.aSh = s.aU = s.aLA = s.aLM = nn * 6; s.adinv = nn;
   s.aIA = s.aIM = nj * 36; s.abeta = nj * 6; s.au = 6 * nn; s.ax = 6 * nn; s.aV = nj * 72;
@@ -304,7 +304,7 @@ static inline void carve_fused(const FusedSizes& s, double* dbl, int* ints, DevB
   b.au = take(s.au); b.ax = take(s.ax); b.aV = take(s.aV);
   int* q = ints;
   auto takei = [&](int64_t k) { int* r = q; q += k * ARB_TILE; return r; };
-  b.factive = takei(s.factive); b.fbranch = takei(s.fbranch);
+  b.factive = takei(s.factive); b.fbranch = takei(s.fbranch); b.fzidx = takei(s.fzidx);
   b.frec = s.total_doubles();
   b.firec = s.total_ints();
 }

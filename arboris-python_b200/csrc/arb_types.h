@@ -110,6 +110,7 @@ struct DevBatch {
   double *ff;        // [nrows]    constraint forces during the sweeps
   double *fRe;       // [ngen][9]  R_e = R_c^T R_body of the contact-aligned generator bodies
   int *factive, *fbranch;  // [nc]
+  int *fzidx;              // [nc][3]  argsort indices of zaligned() of the last prepare stage
   int64_t frec, firec;     // doubles / ints per world in the tiled fused scratch
   // ---- articulated-body factorisation of Z (arb_artic.cuh), [elem][W] ------------------
   double *aX;        // [nj][12]   H_pc of each joint

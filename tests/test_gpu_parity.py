@@ -83,11 +83,18 @@ def test_fused_step_vs_real_reference(torch_cuda, name):
     bw = _batch(model, W)
     gpos, gvel = tr["gpos_in"].T.copy(), tr["gvel_in"].T.copy()
     cf = np.zeros((max(model.nrows, 1), W))
-    worst = {}
+    worst, flips = {}, 0
     for s in range(T):
         bw.set_state(gpos, gvel, cf)
         bw.step(dt, 1)
         g, v, f = bw.get_state()
+        if model.nc:      # active sets, solver branches and signed distances of the FUSED path
+            a = bw.constraints("active").cpu().numpy()
+            br = bw.constraints("branch").cpu().numpy()
+            flips += int((a != tr["active"][:, s]).sum()) + int((br*a != tr["branch"][:, s]).sum())
+            if "sdist" in tr and name == "human36_contact":
+                sd = bw.constraints("sdist").cpu().numpy()[:, :8]
+                worst["sdist"] = max(worst.get("sdist", 0), np.abs(sd - tr["sdist"][:, s][:, :8]).max()*1e-2)
         worst["gvel"] = max(worst.get("gvel", 0), rel(v.T, tr["gvel"][:, s]))
         worst["gpos"] = max(worst.get("gpos", 0), rel(g.T, tr["gpos"][:, s]))
         if model.nrows and name != "ball_socket":
@@ -95,6 +102,7 @@ def test_fused_step_vs_real_reference(torch_cuda, name):
         gpos, gvel = tr["gpos"][:, s].T.copy(), tr["gvel"][:, s].T.copy()
         if model.nrows:
             cf = tr["cforce"][:, s].T.copy()
+    assert flips == 0, "active set / branch flips on the fused path: %d" % flips
     assert int(bw.status().max()) == 0
     for k, v in worst.items():
         assert v <= REL_TOL, (k, v)
@@ -164,6 +172,12 @@ def test_zaligned_indices_bit_exact(torch_cuda):
     o = OracleWorld(model.to_dict())
     o.gpos[:], o.gvel[:] = tr["gpos_in"][0], tr["gvel_in"][0]
     o.update_dynamic(); o.update_controllers(1e-3); o.update_constraints(1e-3)
+    z = bw.constraints("zidx").cpu().numpy()[0]
+    for c in range(8):
+        assert list(z[c]) == list(o.zidx[c])
+    # and from the fused step's own scratch
+    bw.set_state(tr["gpos_in"][:1].T.copy(), tr["gvel_in"][:1].T.copy())
+    bw.step(1e-3, 1)
     z = bw.constraints("zidx").cpu().numpy()[0]
     for c in range(8):
         assert list(z[c]) == list(o.zidx[c])
