@@ -170,6 +170,7 @@ extern "C" int arb_batch_set_option(arb_batch* b, const char* name, int value) {
   if (s == "force_phases") b->force_phases = value;
   else if (s == "prepare_warp") b->prepare_warp = value;
   else if (s == "gs_coop") b->gs_coop = value;
+  else if (s == "sort_period") b->sort_period = value < 0 ? 0 : value;
   else if (s == "time_stages") {
     b->time_stages = value;
     for (int i = 0; i < 4; ++i) b->stage_ms[i] = 0.;
@@ -335,12 +336,12 @@ __global__ void k_gather_int(const int* __restrict__ src, int* __restrict__ out,
 // first, first + stride, ... of the array that starts `off` elements into the record
 template <class T>
 __global__ void k_gather_tiled(const T* __restrict__ src, T* __restrict__ out, int cnt, int stride,
-                               int64_t rec, int64_t w0, int64_t nw) {
+                               int64_t rec, int64_t w0, int64_t nw, const int* __restrict__ slots) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= nw * cnt) return;
   int64_t w = i / cnt;
   int e = (int)(i - w * cnt);
-  const int64_t ww = w0 + w;
+  const int64_t ww = slots ? (int64_t)slots[w0 + w] : w0 + w;   // the scratch belongs to the thread slot
   out[i] = src[(ww / ARB_TILE) * rec * ARB_TILE + (int64_t)e * stride * ARB_TILE + ww % ARB_TILE];
 }
 __global__ void k_get_body(DevModel m, DevBatch b, int which, int body, double* out, int64_t w0, int64_t nw) {
@@ -446,14 +447,15 @@ extern "C" int arb_get_constraint(arb_batch* b, int which, void* out, int64_t w0
   if (b->last_fused) {      // last step ran fused: the quantities live in the tiled fused scratch
     const int cnt = which == ARB_CONS_ZIDX ? 3 * nc : nc;
     const unsigned g = (unsigned)((nw * cnt + 255) / 256);
+    const int* slots = arb_fused_world_slots(b);
     if (which == ARB_CONS_SDIST)
-      k_gather_tiled<double><<<g, 256, 0, b->stream>>>(b->d.faux, (double*)out, nc, 4, b->d.frec, w0, nw);
+      k_gather_tiled<double><<<g, 256, 0, b->stream>>>(b->d.faux, (double*)out, nc, 4, b->d.frec, w0, nw, slots);
     else if (which == ARB_CONS_ACTIVE)
-      k_gather_tiled<int><<<g, 256, 0, b->stream>>>(b->d.factive, (int*)out, nc, 1, b->d.firec, w0, nw);
+      k_gather_tiled<int><<<g, 256, 0, b->stream>>>(b->d.factive, (int*)out, nc, 1, b->d.firec, w0, nw, slots);
     else if (which == ARB_CONS_BRANCH)
-      k_gather_tiled<int><<<g, 256, 0, b->stream>>>(b->d.fbranch, (int*)out, nc, 1, b->d.firec, w0, nw);
+      k_gather_tiled<int><<<g, 256, 0, b->stream>>>(b->d.fbranch, (int*)out, nc, 1, b->d.firec, w0, nw, slots);
     else if (which == ARB_CONS_ZIDX)
-      k_gather_tiled<int><<<g, 256, 0, b->stream>>>(b->d.fzidx, (int*)out, cnt, 1, b->d.firec, w0, nw);
+      k_gather_tiled<int><<<g, 256, 0, b->stream>>>(b->d.fzidx, (int*)out, cnt, 1, b->d.firec, w0, nw, slots);
     else { arb_set_error("unknown constraint quantity"); return -1; }
     LAUNCH_CHECK(b);
     return 0;

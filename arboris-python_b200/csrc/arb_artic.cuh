@@ -39,6 +39,19 @@
 // ST = caller-owned state arrays, [elem][W] (the ABI layout of include/arboris_b200.h).
 #define FT(ptr, idx) (ptr)[(idx) * ARB_TILE]
 #define ST(ptr, idx) (ptr)[(int64_t)(idx) * b.W + w]
+// State reads.  With sorted worlds (arb_fused.cu) the 32 lanes of a warp read 32 different
+// sectors: do not let them allocate in L1, which the stages use as the landing zone of their
+// scratch prefetches.
+ARB_D double arb_ld_state(const double* p) {
+#ifdef __CUDA_ARCH__
+  double v;
+  asm volatile("ld.global.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+#else
+  return *p;
+#endif
+}
+#define ST_LD(ptr, idx) arb_ld_state(&ST(ptr, idx))
 
 // y = X^T x for a wrench x = [m; f], X = Ad(H^-1):  [R m + p x (R f) ; R f]
 ARB_HD void wrench_up(const Se3& h, const double* x, double* y) {
@@ -128,8 +141,8 @@ ARB_D void artic_kinematics(const DevModel& m, const DevBatch& b, int64_t w) {
     const int nd = arb_joint_ndof(type);
     const int dof = m.jdof[j];
     double q[16], dq[6];
-    for (int i = 0; i < arb_joint_ngpos(type); ++i) q[i] = ST(b.gpos, m.jgpos[j] + i);
-    for (int i = 0; i < nd; ++i) dq[i] = ST(b.gvel, dof + i);
+    for (int i = 0; i < arb_joint_ngpos(type); ++i) q[i] = ST_LD(b.gpos, m.jgpos[j] + i);
+    for (int i = 0; i < nd; ++i) dq[i] = ST_LD(b.gvel, dof + i);
     JointKin k;
     joint_kinematics(type, q, dq, k);
     const bool ident = m.hcn_ident[j] != 0;
@@ -217,7 +230,7 @@ ARB_D void artic_kinematics(const DevModel& m, const DevBatch& b, int64_t w) {
 // generalized force of the (diagonal) PD controllers on dof k        (controllers.py:141-159)
 ARB_D double artic_tau(const DevModel& m, const DevBatch& b, int64_t w, int k) {
   if (!m.has_pd || m.pd_gpos[k] < 0) return 0.;
-  return m.pd_kp[k] * (m.pd_qd[k] - ST(b.gpos, m.pd_gpos[k])) + m.pd_c[k];
+  return m.pd_kp[k] * (m.pd_qd[k] - ST_LD(b.gpos, m.pd_gpos[k])) + m.pd_c[k];
 }
 
 // ---------------------------------------------------------------------------------------

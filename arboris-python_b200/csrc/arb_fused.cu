@@ -2,14 +2,38 @@
 // All three stages are lane-per-world (one world per thread); the scratch between them is tiled
 // [W/32][elem][32] (arb_types.h).
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <string>
 
 #include "arb_fused.cuh"
 #include "arb_internal.h"
 
+// World sorting.  The Gauss-Seidel stage is executed warp by warp: a warp pays for a contact
+// visit if ANY of its 32 worlds has that contact active, and for the (5x dearer) sliding-friction
+// solve if any of them slides there.  Which contacts are active / sliding changes slowly from one
+// 1 ms step to the next, so every `sort_period` steps the worlds are re-assigned to threads in the
+// order of the key the last Gauss-Seidel left (contacts that slid, active contacts): warps then hold
+// worlds in the same contact state.  Only the thread <-> world assignment changes; the arithmetic
+// of a world does not depend on its slot, results are bit-identical with and without sorting.
+// While an assignment other than the identity is in force the stages work on a PRIVATE copy of
+// the state laid out by slot ([elem][slot], coalesced like everything else): it is gathered
+// from the caller's arrays (through `perm`) at the start of arb_step and after every re-sort,
+// and scattered back before every re-sort and at the end of arb_step, by two pure copy kernels
+// -- the 32 lanes of a warp never touch 32 different sectors inside the stages.
 struct FusedState {
   double* dbl = nullptr;
   int* ints = nullptr;
+  int* perm[2] = {nullptr, nullptr};          // slot -> world, double-buffered
+  int* inv = nullptr;                         // world -> slot (read-backs), rebuilt on demand
+  unsigned long long* key[2] = {nullptr, nullptr};
+  void* cub_tmp = nullptr;
+  size_t cub_bytes = 0;
+  int cur = 0;
+  bool inv_valid = false;
+  bool sorted = false;                        // an assignment other than the identity is in force
+  int64_t steps = 0;
+  double* pstate = nullptr;                   // private state by slot: gpos, gvel, cforce
+  int* pstatus = nullptr;                     // status bits by slot, merged into the caller's on scatter
 };
 
 #define CUDA_OKF(call)                                                            \
@@ -32,20 +56,28 @@ struct FusedState {
 #ifndef GS_MINBLOCKS
 #define GS_MINBLOCKS 1
 #endif
+// s: thread slot = scratch slot = column of the state arrays the kernel was given (the caller's
+// arrays under the identity assignment, the private by-slot copy otherwise)
+#define FUSED_SLOT_WORLD()                                                  \
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;         \
+  const int64_t w = s
+
 __global__ void __launch_bounds__(FUSED_THREADS, PREP_MINBLOCKS) k_fused_prepare_lane(DevModel m, DevBatch b, double dt) {
-  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= b.W) return;
-  world_fused_prepare(m, fused_tile_view(b, w), w, dt);
+  FUSED_SLOT_WORLD();
+  if (s >= b.W) return;
+  world_fused_prepare(m, fused_tile_view(b, s), w, dt);
 }
 __global__ void __launch_bounds__(FUSED_THREADS, GS_MINBLOCKS) k_fused_gs(DevModel m, DevBatch b, double dt) {
-  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  FUSED_SLOT_WORLD();
+  if (s >= b.W) return;
 #if GS_L_SMEM
   __shared__ double sL[36 * FUSED_THREADS];
-  if (w < b.W) world_fused_gs(m, fused_tile_view(b, w), w, dt, sL + threadIdx.x, FUSED_THREADS);
+  const unsigned long long key = world_fused_gs(m, fused_tile_view(b, s), w, dt, sL + threadIdx.x, FUSED_THREADS);
 #else
   double Lr[36];
-  if (w < b.W) world_fused_gs(m, fused_tile_view(b, w), w, dt, Lr, 1);
+  const unsigned long long key = world_fused_gs(m, fused_tile_view(b, s), w, dt, Lr, 1);
 #endif
+  if (b.fkey != nullptr) b.fkey[s] = key;
 }
 // block-cooperative Gauss-Seidel: the sliding-friction solves of a visit are pooled over the
 // block through shared memory (world_fused_gs_coop)
@@ -65,15 +97,50 @@ __global__ void __launch_bounds__(GS_COOP_THREADS, GS_COOP_MINBLOCKS) k_fused_gs
   co.rs = (int*)(co.bm + 1);                           // [cap]
   co.cnt = co.rs + GS_COOP_CAP;                        // [2]
   co.cap = GS_COOP_CAP; co.tid = threadIdx.x; co.nthr = GS_COOP_THREADS; co.parity = 0;
-  const int64_t w = (int64_t)blockIdx.x * GS_COOP_THREADS + threadIdx.x;
-  const bool valid = w < b.W;
+  FUSED_SLOT_WORLD();
+  const bool valid = s < b.W;
   double Lr[36];     // cached Lambda_FF block: registers (shared memory would shrink the L1)
-  world_fused_gs_coop(m, fused_tile_view(b, valid ? w : b.W - 1), w, valid, dt, co, Lr, 1);
+  const unsigned long long key = world_fused_gs_coop(m, fused_tile_view(b, valid ? s : b.W - 1), w, valid, dt, co, Lr, 1);
+  if (valid && b.fkey != nullptr) b.fkey[s] = key;
 }
 
 __global__ void __launch_bounds__(FUSED_THREADS) k_fused_finish(DevModel m, DevBatch b, double dt) {
-  int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (w < b.W) world_fused_finish(m, fused_tile_view(b, w), w, dt);
+  FUSED_SLOT_WORLD();
+  if (s < b.W) world_fused_finish(m, fused_tile_view(b, s), w, dt);
+}
+
+// private by-slot state <- caller's state (GATHER) or the reverse; one thread per slot and
+// ELEMS_PER_BLOCK_Y elements, the by-slot side coalesced
+#define STATE_EPB 8
+template <bool GATHER>
+__global__ void k_state_copy(double* __restrict__ caller, double* __restrict__ priv, const int* __restrict__ perm,
+                             int nelem, int64_t W) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= W) return;
+  const int64_t w = perm[s];
+  const int e0 = blockIdx.y * STATE_EPB;
+#pragma unroll
+  for (int i = 0; i < STATE_EPB; ++i) {
+    const int e = e0 + i;
+    if (e < nelem) {
+      if (GATHER) priv[(int64_t)e * W + s] = caller[(int64_t)e * W + w];
+      else caller[(int64_t)e * W + w] = priv[(int64_t)e * W + s];
+    }
+  }
+}
+__global__ void k_status_merge(int* __restrict__ caller, int* __restrict__ priv, const int* __restrict__ perm, int64_t W) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= W) return;
+  const int v = priv[s];
+  if (v) { caller[perm[s]] |= v; priv[s] = 0; }
+}
+__global__ void k_iota(int* p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (int)i;
+}
+__global__ void k_invert_perm(const int* __restrict__ perm, int* __restrict__ inv, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) inv[perm[i]] = (int)i;
 }
 
 // the fused stages fold controllers per dof: PD gains must be diagonal (arb_model_host.h)
@@ -89,6 +156,29 @@ static int ensure_fused_scratch(arb_batch* b) {
   CUDA_OKF(cudaMemsetAsync(f->dbl, 0, sizeof(double) * s.total_doubles() * W, b->stream));
   CUDA_OKF(cudaMemsetAsync(f->ints, 0, sizeof(int) * s.total_ints() * W, b->stream));
   carve_fused(s, f->dbl, f->ints, b->d);
+  // world sorting: only models with constraints (the key comes from the Gauss-Seidel stage);
+  // 32-bit world indices
+  if (b->m.nc > 0 && b->d.W < (int64_t)1 << 31) {
+    const int64_t n = b->d.W;
+    for (int i = 0; i < 2; ++i) {
+      CUDA_OKF(cudaMalloc((void**)&f->perm[i], sizeof(int) * n));
+      CUDA_OKF(cudaMalloc((void**)&f->key[i], sizeof(unsigned long long) * n));
+    }
+    CUDA_OKF(cudaMalloc((void**)&f->inv, sizeof(int) * n));
+    CUDA_OKF(cudaMemsetAsync(f->key[0], 0, sizeof(unsigned long long) * n, b->stream));
+    k_iota<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(f->perm[0], n);
+    k_iota<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(f->inv, n);
+    f->inv_valid = true;
+    CUDA_OKF(cub::DeviceRadixSort::SortPairsDescending(nullptr, f->cub_bytes, f->key[0], f->key[1], f->perm[0], f->perm[1],
+                                             (int)n, 0, 64, b->stream));
+    CUDA_OKF(cudaMalloc(&f->cub_tmp, f->cub_bytes ? f->cub_bytes : 1));
+    const HostModel& h = b->model->host;
+    CUDA_OKF(cudaMalloc((void**)&f->pstate, sizeof(double) * (h.ngpos + h.ndof + (h.nrows > 0 ? h.nrows : 1)) * n));
+    CUDA_OKF(cudaMalloc((void**)&f->pstatus, sizeof(int) * n));
+    CUDA_OKF(cudaMemsetAsync(f->pstatus, 0, sizeof(int) * n, b->stream));
+    b->d.perm = f->perm[0];
+    b->d.fkey = f->key[0];
+  }
   CUDA_OKF(cudaFuncSetAttribute(k_fused_gs_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_COOP_SMEM));
   // the per-lane stages live on L1 (operands re-read every sweep / pass): no shared-memory carve-out
   CUDA_OKF(cudaFuncSetAttribute(k_fused_gs, cudaFuncAttributePreferredSharedMemoryCarveout, GS_L_SMEM ? 20 : 0));
@@ -100,29 +190,96 @@ static int ensure_fused_scratch(arb_batch* b) {
 
 
 
+// caller's state <-> private by-slot state through the current assignment
+static int fused_state_sync(arb_batch* b, bool gather) {
+  FusedState* f = b->fused;
+  const HostModel& h = b->model->host;
+  const int64_t W = b->d.W;
+  const int* perm = f->perm[f->cur];
+  double* priv = f->pstate;
+  double* caller[3] = {b->d.gpos, b->d.gvel, b->d.cforce};
+  const int nelem[3] = {h.ngpos, h.ndof, h.nrows};
+  for (int a = 0; a < 3; ++a) {
+    if (nelem[a] > 0) {
+      const dim3 grid((unsigned)((W + 255) / 256), (unsigned)((nelem[a] + STATE_EPB - 1) / STATE_EPB));
+      if (gather) k_state_copy<true><<<grid, 256, 0, b->stream>>>(caller[a], priv, perm, nelem[a], W);
+      else k_state_copy<false><<<grid, 256, 0, b->stream>>>(caller[a], priv, perm, nelem[a], W);
+      b->launches += 1;
+    }
+    priv += (int64_t)(a == 2 ? 0 : nelem[a]) * W;
+  }
+  if (!gather) {
+    k_status_merge<<<(unsigned)((W + 255) / 256), 256, 0, b->stream>>>(b->d.status, f->pstatus, perm, W);
+    b->launches += 1;
+  }
+  return 0;
+}
+
 int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
   int rc = ensure_fused_scratch(b);
   if (rc) return rc;
-  const unsigned g = (unsigned)((b->d.W + FUSED_THREADS - 1) / FUSED_THREADS);
+  FusedState* f = b->fused;
+  const HostModel& h = b->model->host;
+  const int64_t W = b->d.W;
+  const unsigned g = (unsigned)((W + FUSED_THREADS - 1) / FUSED_THREADS);
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   if (b->time_stages)
     for (int i = 0; i < 4; ++i) CUDA_OKF(cudaEventCreate(&ev[i]));
+  if (f->sorted && b->sort_period <= 0) {       // sorting switched off: back to the identity
+    k_iota<<<(unsigned)((W + 255) / 256), 256, 0, b->stream>>>(f->perm[f->cur], W);
+    f->sorted = false;
+    f->inv_valid = false;
+  }
+  // the batch the stages see: the caller's state arrays under the identity assignment,
+  // the private by-slot copy otherwise
+  DevBatch d = b->d;
+  auto point_at_private = [&]() {
+    d.gpos = f->pstate;
+    d.gvel = d.gpos + (int64_t)h.ngpos * W;
+    d.cforce = d.gvel + (int64_t)h.ndof * W;
+    d.status = f->pstatus;
+  };
+  if (f->sorted) {
+    rc = fused_state_sync(b, true);
+    if (rc) return rc;
+    point_at_private();
+  }
   for (int s = 0; s < nsteps; ++s) {
     const double dt = dts[s];
     if (!(dt > 0)) { arb_set_error("dt must be > 0"); return -3; }
+    if (f->perm[0] != nullptr && b->sort_period > 0 && f->steps > 0 && (f->steps % b->sort_period) == 0) {
+      // re-assign worlds to threads by the key of the previous step, DESCENDING: the CTAs of the
+      // worlds with the most contact work are dispatched first and the grid's tail is made of the
+      // cheap ones (stable: ties keep their order).  Done BEFORE the step, so that after a step the scratch read-backs
+      // (arb_get_constraint) still see the assignment the step ran with.
+      if (f->sorted) fused_state_sync(b, false);
+      const int nb = b->m.nc < 32 ? b->m.nc : 32;
+      const int c = f->cur;
+      CUDA_OKF(cub::DeviceRadixSort::SortPairsDescending(f->cub_tmp, f->cub_bytes, f->key[c], f->key[c ^ 1], f->perm[c],
+                                               f->perm[c ^ 1], (int)W, 0, 2 * nb, b->stream));
+      f->cur = c ^ 1;
+      b->d.perm = d.perm = f->perm[f->cur];
+      b->d.fkey = d.fkey = f->key[f->cur];     // (the sorted keys are overwritten by the next Gauss-Seidel)
+      f->inv_valid = false;
+      f->sorted = true;
+      b->launches += 1;
+      fused_state_sync(b, true);
+      point_at_private();
+    }
     if (ev[0]) cudaEventRecord(ev[0], b->stream);
-    k_fused_prepare_lane<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    k_fused_prepare_lane<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, d, dt);
     if (ev[0]) cudaEventRecord(ev[1], b->stream);
     if (b->m.nc > 0) {
       if (b->m.nc <= 64 && b->gs_coop)
-        k_fused_gs_coop<<<(unsigned)((b->d.W + GS_COOP_THREADS - 1) / GS_COOP_THREADS), GS_COOP_THREADS,
-                          GS_COOP_SMEM, b->stream>>>(b->m, b->d, dt);
+        k_fused_gs_coop<<<(unsigned)((W + GS_COOP_THREADS - 1) / GS_COOP_THREADS), GS_COOP_THREADS,
+                          GS_COOP_SMEM, b->stream>>>(b->m, d, dt);
       else
-        k_fused_gs<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+        k_fused_gs<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, d, dt);
     }
     if (ev[0]) cudaEventRecord(ev[2], b->stream);
-    k_fused_finish<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    k_fused_finish<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, d, dt);
     b->launches += (b->m.nc > 0) ? 3 : 2;
+    ++f->steps;
     if (ev[0]) {   // diagnostic mode: per-stage device time of this step
       cudaEventRecord(ev[3], b->stream);
       CUDA_OKF(cudaEventSynchronize(ev[3]));
@@ -134,6 +291,7 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
       b->stage_ms[3] += 1.;
     }
   }
+  if (f->sorted) fused_state_sync(b, false);
   for (int i = 0; i < 4; ++i)
     if (ev[i]) cudaEventDestroy(ev[i]);
   cudaError_t e = cudaGetLastError();
@@ -141,10 +299,27 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
   return 0;
 }
 
+// world -> slot map of the current assignment (device pointer), or nullptr for the identity
+const int* arb_fused_world_slots(arb_batch* b) {
+  FusedState* f = b->fused;
+  if (!f || !f->perm[0]) return nullptr;
+  if (!f->inv_valid) {
+    const int64_t n = b->d.W;
+    k_invert_perm<<<(unsigned)((n + 255) / 256), 256, 0, b->stream>>>(f->perm[f->cur], f->inv, n);
+    f->inv_valid = true;
+  }
+  return f->inv;
+}
+
 void arb_fused_release(arb_batch* b) {
   if (!b->fused) return;
   cudaFree(b->fused->dbl);
   cudaFree(b->fused->ints);
+  for (int i = 0; i < 2; ++i) { cudaFree(b->fused->perm[i]); cudaFree(b->fused->key[i]); }
+  cudaFree(b->fused->inv);
+  cudaFree(b->fused->cub_tmp);
+  cudaFree(b->fused->pstate);
+  cudaFree(b->fused->pstatus);
   delete b->fused;
   b->fused = nullptr;
 }

@@ -181,7 +181,7 @@ ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, 
     if (type == ARB_CONS_JOINT_LIMITS) {
       Se3 I;
       se3_identity(I);
-      act = constraint_update(m, c, I, I, nullptr, nullptr, ST(b.gpos, ci[2]), dt, aux, T1, T0, zi);
+      act = constraint_update(m, c, I, I, nullptr, nullptr, ST_LD(b.gpos, ci[2]), dt, aux, T1, T0, zi);
       ST(b.cforce, r0) = 0.;
     } else {
       Se3 P0, P1;
@@ -504,9 +504,10 @@ ARB_D int softfinger_solve_tiled(const double* v, const double* pA, const double
 
 // one visit of a constraint whose rows depend on ONE generator body (the other frame is on
 // the ground): ND rows, block in the cache
+// returns the solver branch (soft-finger contacts; 0 otherwise)
 template <int ND>
-ARB_D void gs_visit_one_body(const DevModel& m, const DevBatch& b, int64_t w, int c, double dt,
-                             GsCache& k, int* status) {
+ARB_D int gs_visit_one_body(const DevModel& m, const DevBatch& b, int64_t w, int c, double dt,
+                            GsCache& k, int* status) {
   const int type = m.ctype[c];
   const double* cd = m.cdbl + ARB_CONS_NDBL * c;
   const int r0 = m.crow[c];
@@ -516,6 +517,7 @@ ARB_D void gs_visit_one_body(const DevModel& m, const DevBatch& b, int64_t w, in
   double* pf = b.ff + r0 * ARB_TILE;
   const double* paux = b.faux + c * (4 * ARB_TILE);
   const bool al = ND == 4 && m.caligned[c] != 0;
+  int br = 0;
   double v[4], f[ND], df[4];
   if (al) {
     gs_aligned_rows(Tp, k.u, v);
@@ -545,8 +547,8 @@ ARB_D void gs_visit_one_body(const DevModel& m, const DevBatch& b, int64_t w, in
       pf[i * ARB_TILE] = f[i] + df[i];
     }
   } else {
-    const int br = softfinger_solve_tiled(v, b.fAcc + r0 * (4 * ARB_TILE), b.fP + r0 * (4 * ARB_TILE),
-                                          paux[0], cd[36], cd + 37, dt, f, df, status);
+    br = softfinger_solve_tiled(v, b.fAcc + r0 * (4 * ARB_TILE), b.fP + r0 * (4 * ARB_TILE),
+                                paux[0], cd[36], cd + 37, dt, f, df, status);
 #pragma unroll
     for (int i = 0; i < ND; ++i) pf[i * ARB_TILE] = f[i];
     b.fbranch[c * ARB_TILE] = br;
@@ -573,6 +575,7 @@ ARB_D void gs_visit_one_body(const DevModel& m, const DevBatch& b, int64_t w, in
     for (int p = 0; p < 6; ++p) acc += GSL(k, 6 * q + p) * wv[p];
     k.u[q] += acc;
   }
+  return br;
 }
 
 // diagonal Delassus block A_cc = T Lambda_FF T^T of a one-body constraint and its pseudo-inverse
@@ -724,17 +727,27 @@ ARB_D void gs_visit_limit(const DevModel& m, const DevBatch& b, int c, double dt
   }
 }
 
-ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, double dt, double* Lstore,
-                          int Lstride) {
+#ifdef ARB_HOSTTEST_COUNTERS
+static unsigned* arb_dbg_slidemask = nullptr;   // host unit tests only: [W][sweeps] mask of contacts that slid
+#endif
+// Returns the world's sort key for the next steps (arb_fused.cu): contacts that took the sliding
+// branch in some sweep (high part) and active constraints (low part), first 32 constraints.
+ARB_D unsigned long long gs_sort_key(const DevModel& m, unsigned slid, unsigned amask) {
+  const int nb = m.nc < 32 ? m.nc : 32;
+  return ((unsigned long long)slid << nb) | (unsigned long long)amask;
+}
+ARB_D unsigned long long world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, double dt,
+                                        double* Lstore, int Lstride) {
   const int NG = m.ngrows;
   int status = 0;
+  unsigned slid = 0u;
   bool any = false;
   for (int c = 0; c < m.nc; ++c) any = any || FT(b.factive, c);
   for (int g = 0; g < NG; ++g) FT(b.fy, g) = 0.;
-  if (!any) return;
+  if (!any) return 0ull;
   // constraint forces live in tiled scratch during the sweeps (ball-and-socket rows carry
   // the warm start, the others were reset by the prepare stage)
-  for (int r = 0; r < m.nrows; ++r) FT(b.ff, r) = ST(b.cforce, r);
+  for (int r = 0; r < m.nrows; ++r) FT(b.ff, r) = ST_LD(b.cforce, r);
   GsCache k;
   k.g = -1;
   k.n = 0;
@@ -780,12 +793,16 @@ ARB_D void world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, doubl
       if (!act) continue;
       if (c + 1 < m.nc) gs_prefetch_visit(m, b, c + 1);
       if (type == ARB_CONS_BALL_SOCKET) gs_visit_one_body<3>(m, b, w, c, dt, k, &status);
-      else gs_visit_one_body<4>(m, b, w, c, dt, k, &status);
+      else if (gs_visit_one_body<4>(m, b, w, c, dt, k, &status) == 3 && c < 32) slid |= 1u << c;
+#ifdef ARB_HOSTTEST_COUNTERS
+      if (arb_dbg_slidemask && c < 32 && FT(b.fbranch, c) == 3) arb_dbg_slidemask[w * ARB_GS_SWEEPS + sweep] |= 1u << c;
+#endif
     }
   }
   gs_cache_flush(m, b, w, k);
   for (int r = 0; r < m.nrows; ++r) ST(b.cforce, r) = FT(b.ff, r);
   if (status) b.status[w] |= status;
+  return gs_sort_key(m, slid, amask);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -980,10 +997,11 @@ ARB_D void gs_softfinger_end(const DevModel& m, const DevBatch& b, int c, GsCach
 
 // `valid`: this thread has a world (w < W); threads without one only take part in the barriers.
 // Supports up to 64 constraints (the active set is a bit mask).
-ARB_D void world_fused_gs_coop(const DevModel& m, const DevBatch& b, int64_t w, bool valid, double dt,
-                               GsCoop& co, double* Lstore, int Lstride) {
+ARB_D unsigned long long world_fused_gs_coop(const DevModel& m, const DevBatch& b, int64_t w, bool valid,
+                                             double dt, GsCoop& co, double* Lstore, int Lstride) {
   const int NG = m.ngrows;
   int status = 0;
+  unsigned slid = 0u;
   unsigned long long amask = 0ull;
   if (valid) {
     for (int c = 0; c < m.nc; ++c)
@@ -995,7 +1013,7 @@ ARB_D void world_fused_gs_coop(const DevModel& m, const DevBatch& b, int64_t w, 
   coop_or(co.bm, amask);
   coop_sync();
   const unsigned long long bm = *co.bm;
-  if (bm == 0ull) return;                    // no world of this block has an active constraint
+  if (bm == 0ull) return 0ull;               // no world of this block has an active constraint
   const bool live = amask != 0ull;
   GsCache k;
   k.g = -1;
@@ -1003,7 +1021,7 @@ ARB_D void world_fused_gs_coop(const DevModel& m, const DevBatch& b, int64_t w, 
   k.L = Lstore;
   k.ls = Lstride;
   if (live) {
-    for (int r = 0; r < m.nrows; ++r) FT(b.ff, r) = ST(b.cforce, r);
+    for (int r = 0; r < m.nrows; ++r) FT(b.ff, r) = ST_LD(b.cforce, r);
     gs_prologue(m, b, w);
   }
   k.g = -1;
@@ -1043,6 +1061,7 @@ ARB_D void world_fused_gs_coop(const DevModel& m, const DevBatch& b, int64_t w, 
       }
       coop_solve_sliding(co, m.cdbl + ARB_CONS_NDBL * c + 37);
       if (act) gs_softfinger_end(m, b, c, k, co, br, slot, f, df, &status);
+      if (br == 3 && c < 32) slid |= 1u << c;
     }
   }
   if (live) {
@@ -1050,6 +1069,7 @@ ARB_D void world_fused_gs_coop(const DevModel& m, const DevBatch& b, int64_t w, 
     for (int r = 0; r < m.nrows; ++r) ST(b.cforce, r) = FT(b.ff, r);
     if (status) b.status[w] |= status;
   }
+  return gs_sort_key(m, slid, (unsigned)(amask & 0xffffffffull));
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1063,20 +1083,23 @@ ARB_D void world_fused_finish(const DevModel& m, const DevBatch& b, int64_t w, d
     artic_forward_full<true>(m, b, w, b.au, b.ax);
   }
   bool finite = true;
-  for (int i = 0; i < n; ++i) {
-    double t = FT(b.fq, i);
-    if (any) t += FT(b.ax, i);
-    ST(b.gvel, i) = t;
-    finite = finite && isfinite(t);
-  }
   for (int j = 0; j < m.nj; ++j) {
     const int type = m.jtype[j];
     const int g = m.jgpos[j], d = m.jdof[j];
+    const int nd = arb_joint_ndof(type);
+    double nv[6];
+    for (int i = 0; i < nd; ++i) {
+      double t = FT(b.fq, d + i);
+      if (any) t += FT(b.ax, d + i);
+      ST(b.gvel, d + i) = t;
+      finite = finite && isfinite(t);
+      nv[i] = t;
+    }
     if (type == ARB_JOINT_FREE) {
       double q[16], tw[6];
-      for (int i = 0; i < 16; ++i) q[i] = ST(b.gpos, g + i);
+      for (int i = 0; i < 16; ++i) q[i] = ST_LD(b.gpos, g + i);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) tw[i] = dt * ST(b.gvel, d + i);
+      for (int i = 0; i < 6; ++i) tw[i] = dt * nv[i];
       Se3 H, E, R;
       se3_from16(q, H);
       se3_exp(tw, E);
@@ -1088,8 +1111,7 @@ ARB_D void world_fused_finish(const DevModel& m, const DevBatch& b, int64_t w, d
         ST(b.gpos, g + 4 * r + 3) = R.p[r];
       }
     } else {
-      const int nd = arb_joint_ndof(type);
-      for (int i = 0; i < nd; ++i) ST(b.gpos, g + i) += dt * ST(b.gvel, d + i);
+      for (int i = 0; i < nd; ++i) ST(b.gpos, g + i) = ST_LD(b.gpos, g + i) + dt * nv[i];
     }
   }
   if (!finite) b.status[w] |= ARB_STATUS_NONFINITE;

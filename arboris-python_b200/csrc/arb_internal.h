@@ -32,6 +32,7 @@ struct arb_batch {
   int time_stages = 0;             // 1: CUDA events around every fused stage (diagnostic, synchronises per step)
   double stage_ms[4] = {0., 0., 0., 0.};   // accumulated prepare / gs / finish milliseconds, [3] = steps timed
   FusedState* fused = nullptr;
+  int sort_period = 2;             // fused path: re-sort the worlds by contact state every N steps (0: never)
   int last_fused = 0;              // 1: the constraint read-backs come from the fused scratch (last step was fused)
 };
 
@@ -42,3 +43,4 @@ int arb_ensure_phase_scratch(arb_batch* b);
 bool arb_fused_supported(const arb_batch* b);
 int arb_fused_step(arb_batch* b, const double* dts, int nsteps);
 void arb_fused_release(arb_batch* b);
+const int* arb_fused_world_slots(arb_batch* b);

@@ -112,6 +112,10 @@ struct DevBatch {
   int *factive, *fbranch;  // [nc]
   int *fzidx;              // [nc][3]  argsort indices of zaligned() of the last prepare stage
   int64_t frec, firec;     // doubles / ints per world in the tiled fused scratch
+  // world sorting (arb_fused.cu): the thread (and scratch slot) s works on world perm[s]; the
+  // Gauss-Seidel stage leaves a sort key per slot (contacts that slid, active contacts)
+  const int *perm;              // [W] slot -> world, or nullptr (identity)
+  unsigned long long *fkey;     // [W] by slot, or nullptr
   // ---- articulated-body factorisation of Z (arb_artic.cuh), [elem][W] ------------------
   double *aX;        // [nj][12]   H_pc of each joint
   double *atw, *ath; // [nj][6]    body twist T_b and the accumulated joint term theta_b

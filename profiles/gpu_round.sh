@@ -7,7 +7,7 @@ python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "p
 tail -3 gpurun_out/${TAG}_pytest.log
 python bench.py --steps 100 --warmup 10 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench exit $?"
 cat gpurun_out/${TAG}_bench.json
-ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 900 -c 300 --csv \
+ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1000 -c 300 --csv \
     --log-file gpurun_out/${TAG}_launches.csv python bench.py --worlds 65536 --steps 20 --warmup 3 --no-e2e --no-cpu-baseline \
     > gpurun_out/${TAG}_launches.log 2>&1
 for k in gs prepare finish; do
