@@ -242,6 +242,11 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
   // through its slow path (a quarter of this stage's instructions before)
   const double idt = 1. / dt;
   const double gt[6] = {0., 0., 0., m.gravity * m.up[0], m.gravity * m.up[1], m.gravity * m.up[2]};
+  // Along a chain (joint j+1 hangs on the body of joint j, the usual case in depth-first order) the
+  // child's contribution X^T IA X, X^T IM X, X^T beta stays in registers for the next iteration
+  // instead of going through its scratch slot: `carry`.
+  double IA[36], IM[36], beta[6];
+  bool carry = false;
   for (int j = m.nj - 1; j >= 0; --j) {
     if (j > 0) {
       arb_prefetch_rows<6>(b.atw + (j - 1) * (6 * ARB_TILE));
@@ -256,7 +261,12 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
     const int dof = m.jdof[j];
     const int flags = m.bflags[j];
     const double* Mb = m.bmass + 36 * j;
-    double IA[36], IM[36], beta[6];
+    if (!carry) {
+#pragma unroll
+      for (int i = 0; i < 36; ++i) { IA[i] = 0.; IM[i] = 0.; }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) beta[i] = 0.;
+    }
     double T[6], th[6];
 #pragma unroll
     for (int i = 0; i < 6; ++i) { T[i] = FT(b.atw, j * 6 + i); th[i] = FT(b.ath, j * 6 + i); }
@@ -279,7 +289,7 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
         m3_mulv(X3, bot, x2);
         cross3(T, bot, d);
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { IA[6 * i + c] = a[i] + x2[i]; IA[6 * (i + 3) + c] = d[i]; }
+        for (int i = 0; i < 3; ++i) { IA[6 * i + c] += a[i] + x2[i]; IA[6 * (i + 3) + c] += d[i]; }
       }
 #pragma unroll
       for (int r = 0; r < 6; ++r) {  // M adjacency(theta), row by row: [a1 x w + a2 x v, a2 x w]
@@ -293,7 +303,7 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
         for (int i = 0; i < 3; ++i) { IA[6 * r + i] += c1[i] + c2[i]; IA[6 * r + 3 + i] += c3[i]; }
       }
 #pragma unroll
-      for (int i = 0; i < 36; ++i) { IA[i] += Mb[i] * idt; IM[i] = Mb[i]; }
+      for (int i = 0; i < 36; ++i) { IA[i] += Mb[i] * idt; IM[i] += Mb[i]; }
       // -w_b = -M_b (T/dt + gravity_b)
       double a[6];
 #pragma unroll
@@ -311,13 +321,8 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
         double t = 0.;
 #pragma unroll
         for (int c = 0; c < 6; ++c) t += Mb[6 * r + c] * a[c];
-        beta[r] = -t;
+        beta[r] -= t;
       }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 36; ++i) { IA[i] = 0.; IM[i] = 0.; }
-#pragma unroll
-      for (int i = 0; i < 6; ++i) beta[i] = 0.;
     }
     if (flags & ARB_BODY_HASVISC) {
       const double* Bb = m.bvisc + 36 * j;
@@ -327,6 +332,7 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
     // children's contributions: every child joint c left X^T IA X, X^T IM X, X^T beta in ITS
     // OWN slot (no read-modify-write on the way up), summed here
     for (int c = m.jchild0[j]; c >= 0; c = m.jsib[c]) {
+      if (carry && c == j + 1) continue;        // already in IA, IM, beta
       const double* pa = b.aIA + c * (36 * ARB_TILE);
       const double* pm = b.aIM + c * (36 * ARB_TILE);
       const double* pb = b.abeta + c * (6 * ARB_TILE);
@@ -382,13 +388,21 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
       congruence_up(X, IM);
       double bu[6];
       wrench_up(X, beta, bu);
-      double* pa = b.aIA + j * (36 * ARB_TILE);
-      double* pm = b.aIM + j * (36 * ARB_TILE);
-      double* pb = b.abeta + j * (6 * ARB_TILE);
+      carry = (par == j);       // the parent body is the one of joint j-1: next iteration
+      if (carry) {
 #pragma unroll
-      for (int i = 0; i < 36; ++i) { pa[i * ARB_TILE] = IA[i]; pm[i * ARB_TILE] = IM[i]; }
+        for (int i = 0; i < 6; ++i) beta[i] = bu[i];
+      } else {
+        double* pa = b.aIA + j * (36 * ARB_TILE);
+        double* pm = b.aIM + j * (36 * ARB_TILE);
+        double* pb = b.abeta + j * (6 * ARB_TILE);
 #pragma unroll
-      for (int i = 0; i < 6; ++i) pb[i * ARB_TILE] = bu[i];
+        for (int i = 0; i < 36; ++i) { pa[i * ARB_TILE] = IA[i]; pm[i * ARB_TILE] = IM[i]; }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) pb[i * ARB_TILE] = bu[i];
+      }
+    } else {
+      carry = false;
     }
   }
   return ok;
