@@ -144,6 +144,22 @@ class BatchedWorld(object):
             self._batch_h, dts.ctypes.data_as(_capi.c_dblp), len(dts)))
         self._current_time += float(dts.sum())
 
+    def begin_step(self, dt):
+        """First half of one fused step: everything ``simulate()`` does before the observers
+        run (update_dynamic, update_controllers, update_constraints; core.py:1357-1359).  The
+        state is untouched; body poses / twists, active sets and constraint forces of this
+        step can be read until ``end_step``."""
+        assert dt > 0
+        self._sync_stream()
+        _capi.check(self._lib, self._lib.arb_step_begin(self._batch_h, float(dt)))
+
+    def end_step(self, dt):
+        """Second half: ``integrate(dt)`` (core.py:1362)."""
+        assert dt > 0
+        self._sync_stream()
+        _capi.check(self._lib, self._lib.arb_step_end(self._batch_h, float(dt)))
+        self._current_time += dt
+
     def step_host(self, gpos, gvel, cforce, dt, nsteps=1):
         """End-to-end call with HOST buffers (numpy (elem, W), updated in place):
         host->device copy of the state, ``nsteps`` steps, device->host copy."""

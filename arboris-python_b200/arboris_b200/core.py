@@ -547,13 +547,30 @@ def simulate(world, timeline, observers=()):
     world.init()
     for obs in observers:
         obs.init(world, timeline)
+    # A batched world keeps the fused CUDA step when every observer only reads what the fused
+    # step leaves behind (state, body poses / twists, constraint forces and active sets):
+    # begin_step = the three update_* phases, end_step = integrate.  Without observers whole
+    # runs of steps go to the device in one call.
+    fused = hasattr(world, "begin_step") and all(getattr(o, "fused_ok", False) for o in observers)
+    if fused and not observers:
+        import numpy as _np
+        dts = _np.diff(_np.asarray(timeline, dtype=float))
+        if len(dts):
+            world.step(dts)
+        return
     for next_time in timeline[1:]:
         dt = next_time - world._current_time
-        world.update_dynamic()
-        world.update_controllers(dt)
-        world.update_constraints(dt)
+        if fused:
+            world.begin_step(dt)
+        else:
+            world.update_dynamic()
+            world.update_controllers(dt)
+            world.update_constraints(dt)
         for obs in observers:
             obs.update(dt)
-        world.integrate(dt)
+        if fused:
+            world.end_step(dt)
+        else:
+            world.integrate(dt)
     for obs in observers:
         obs.finish()

@@ -232,6 +232,8 @@ extern "C" int arb_update_dynamic(arb_batch* b) {
   rc = arb_ensure_phase_scratch(b); if (rc) return rc;
   k_update_dynamic<<<lpw_grid(b->d.W), LPW_THREADS, 0, b->stream>>>(b->m, b->d);
   LAUNCH_CHECK(b);
+  b->last_fused = 0;
+  b->half_open = 0;
   return 0;
 }
 extern "C" int arb_update_controllers(arb_batch* b, double dt) {
@@ -290,6 +292,28 @@ extern "C" int arb_step(arb_batch* b, const double* dts, int nsteps) {
   rc = arb_fused_step(b, dts, nsteps);
   if (rc == 0 && nsteps > 0) b->last_fused = 1;
   return rc;
+}
+
+extern "C" int arb_step_begin(arb_batch* b, double dt) {
+  int rc = check_bound(b); if (rc) return rc;
+  if (!(dt > 0)) { arb_set_error("dt must be > 0"); return -3; }
+  CUDA_OK(cudaSetDevice(b->device));
+  if (b->force_phases || !arb_fused_supported(b)) {
+    rc = arb_update_dynamic(b); if (rc) return rc;
+    rc = arb_update_controllers(b, dt); if (rc) return rc;
+    return arb_update_constraints(b, dt);
+  }
+  rc = arb_fused_step_half(b, dt, 0);
+  if (rc == 0) { b->last_fused = 1; b->half_open = 1; }
+  return rc;
+}
+extern "C" int arb_step_end(arb_batch* b, double dt) {
+  int rc = check_bound(b); if (rc) return rc;
+  if (!(dt > 0)) { arb_set_error("dt must be > 0"); return -3; }
+  CUDA_OK(cudaSetDevice(b->device));
+  if (!b->half_open) return arb_integrate(b, dt);   // arb_step_begin ran the phase kernels
+  b->half_open = 0;
+  return arb_fused_step_half(b, dt, 1);
 }
 
 extern "C" int arb_step_host(arb_batch* b, double* h_gpos, double* h_gvel, double* h_cforce,
@@ -428,12 +452,43 @@ extern "C" int arb_get_vector(arb_batch* b, int which, double* out, int64_t w0, 
   LAUNCH_CHECK(b);
   return 0;
 }
+// pose (4x4 row-major) / twist of a body from the fused scratch (fpose [nj][12], atw [nj][6])
+__global__ void k_get_body_fused(DevBatch b, int which, int body, double* __restrict__ out, int64_t w0, int64_t nw,
+                                 const int* __restrict__ slots) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nw) return;
+  const int64_t s = slots ? (int64_t)slots[w0 + i] : w0 + i;
+  const int64_t base = (s / ARB_TILE) * b.frec * ARB_TILE + s % ARB_TILE;
+  if (which == ARB_BODY_POSE) {
+    double* o = out + i * 16;
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c)
+        o[4 * r + c] = body == 0 ? (r == c ? 1. : 0.) : b.fpose[base + (int64_t)((body - 1) * 12 + 3 * r + c) * ARB_TILE];
+      o[4 * r + 3] = body == 0 ? 0. : b.fpose[base + (int64_t)((body - 1) * 12 + 9 + r) * ARB_TILE];
+    }
+    o[12] = o[13] = o[14] = 0.; o[15] = 1.;
+  } else {
+    for (int r = 0; r < 6; ++r)
+      out[i * 6 + r] = body == 0 ? 0. : b.atw[base + (int64_t)((body - 1) * 6 + r) * ARB_TILE];
+  }
+}
 extern "C" int arb_get_body(arb_batch* b, int which, int body, double* out, int64_t w0, int64_t w1) {
-  int rc = check_range(b, out, w0, w1); if (rc) return rc;
+  const bool from_fused = b && b->last_fused && (which == ARB_BODY_POSE || which == ARB_BODY_TWIST);
+  int rc = check_range(b, out, w0, w1, from_fused); if (rc) return rc;
   CUDA_OK(cudaSetDevice(b->device));
   if (body < 0 || body > b->m.nj) { arb_set_error("body index out of range"); return -1; }
   if (which < ARB_BODY_POSE || which > ARB_BODY_NLE) { arb_set_error("unknown body quantity"); return -1; }
   const int64_t nw = w1 - w0;
+  if (from_fused) {
+    k_get_body_fused<<<(unsigned)((nw + 127) / 128), 128, 0, b->stream>>>(b->d, which, body, out, w0, nw,
+                                                                          arb_fused_world_slots(b));
+    LAUNCH_CHECK(b);
+    return 0;
+  }
+  if (b->last_fused) {
+    arb_set_error("jacobian / djacobian / nleffects are not formed by the fused step: call arb_update_dynamic first");
+    return -2;
+  }
   k_get_body<<<(unsigned)((nw + 127) / 128), 128, 0, b->stream>>>(b->m, b->d, which, body, out, w0, nw);
   LAUNCH_CHECK(b);
   return 0;

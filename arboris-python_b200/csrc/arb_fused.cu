@@ -299,6 +299,33 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
   return 0;
 }
 
+// One step in two halves (arb_step_begin / arb_step_end): identity assignment, the caller's
+// state arrays, so that everything the caller reads between the halves is in place.
+int arb_fused_step_half(arb_batch* b, double dt, int half) {
+  int rc = ensure_fused_scratch(b);
+  if (rc) return rc;
+  FusedState* f = b->fused;
+  const int64_t W = b->d.W;
+  const unsigned g = (unsigned)((W + FUSED_THREADS - 1) / FUSED_THREADS);
+  if (f->sorted) {
+    k_iota<<<(unsigned)((W + 255) / 256), 256, 0, b->stream>>>(f->perm[f->cur], W);
+    f->sorted = false;
+    f->inv_valid = false;
+  }
+  if (half == 0) {
+    k_fused_prepare_lane<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    if (b->m.nc > 0) k_fused_gs<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    b->launches += (b->m.nc > 0) ? 2 : 1;
+  } else {
+    k_fused_finish<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    b->launches += 1;
+    ++f->steps;
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { arb_set_error(std::string("kernel launch: ") + cudaGetErrorString(e)); return -101; }
+  return 0;
+}
+
 // world -> slot map of the current assignment (device pointer), or nullptr for the identity
 const int* arb_fused_world_slots(arb_batch* b) {
   FusedState* f = b->fused;

@@ -33,6 +33,7 @@ struct arb_batch {
   double stage_ms[4] = {0., 0., 0., 0.};   // accumulated prepare / gs / finish milliseconds, [3] = steps timed
   FusedState* fused = nullptr;
   int sort_period = 2;             // fused path: re-sort the worlds by contact state every N steps (0: never)
+  int half_open = 0;               // arb_step_begin ran the fused stages: arb_step_end must run the finish stage
   int last_fused = 0;              // 1: the constraint read-backs come from the fused scratch (last step was fused)
 };
 
@@ -44,3 +45,4 @@ bool arb_fused_supported(const arb_batch* b);
 int arb_fused_step(arb_batch* b, const double* dts, int nsteps);
 void arb_fused_release(arb_batch* b);
 const int* arb_fused_world_slots(arb_batch* b);
+int arb_fused_step_half(arb_batch* b, double dt, int half);   // 0: prepare + gs, 1: finish

@@ -149,6 +149,13 @@ int arb_integrate(arb_batch *batch, double dt);
 /* replaces the simulate() loop body (core.py:1356-1363) for nsteps consecutive steps
  * of length dts[i] (HOST array); intermediate matrices stay on chip */
 int arb_step(arb_batch *batch, const double *dts, int nsteps);
+/* the same step in two halves, for callers that observe the world between
+ * update_constraints and integrate like the reference's Observer.update (core.py:1360-1362):
+ * arb_step_begin = update_dynamic + update_controllers + update_constraints (state untouched,
+ * constraint forces written), arb_step_end = integrate.  Between the two, arb_get_body
+ * (POSE, TWIST) and arb_get_constraint read the step's quantities. */
+int arb_step_begin(arb_batch *batch, double dt);
+int arb_step_end(arb_batch *batch, double dt);
 /* same, with HOST state buffers (same layouts): H2D, nsteps, D2H, synchronous */
 int arb_step_host(arb_batch *batch, double *h_gpos, double *h_gvel, double *h_cforce,
                   const double *dts, int nsteps);

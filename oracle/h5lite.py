@@ -113,6 +113,8 @@ class _File(object):
                     assert ver in (1, 2) and self.b[body + 2] == 1
                     addr = self.u(body + 8, 8)
         n = int(np.prod(shape)) if shape else 1
+        if n == 0:     # no storage allocated (address undefined)
+            return np.zeros(shape)
         return np.frombuffer(self.b, dtype=dtype, count=n, offset=addr).reshape(shape).copy()
 
 
