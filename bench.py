@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.)
+    ap.add_argument("--e2e-chunks", type=int, default=8,
+                    help="column blocks (each on its own stream) of the end-to-end pass; 1 = one "
+                         "synchronous arb_step_host call per step")
     ap.add_argument("--opt", action="append", help="arb_batch_set_option switch, name=value (A/B runs)")
     return ap.parse_args()
 
@@ -181,7 +184,7 @@ def run_ours(a):
     import torch
     import torch.distributed as dist
     from arboris_b200 import scenarios, _capi
-    from arboris_b200.batch import BatchedWorld
+    from arboris_b200.batch import BatchedWorld, HostPipeline
     from arboris_b200.flatten import flatten
     from arboris_b200.shard import env_rank, shard_range, reduce_report
 
@@ -253,9 +256,21 @@ def run_ours(a):
         hep.blocks, hep.t = ep.blocks, ep.t
         hep.state, hep.init = (hg, hv, hf), (torch.as_tensor(gp), torch.as_tensor(gv), None)
 
+        pipe = None
+        if a.e2e_chunks > 1:
+            # the public end-to-end call: column blocks of the host state, one stream each, so
+            # that copies and kernels of different blocks overlap (batch.HostPipeline)
+            pipe = HostPipeline(model, W, chunks=a.e2e_chunks, device=bw.device)
+            for opt in (a.opt or []):
+                name, val = opt.split("=")
+                pipe.set_option(name, int(val))
+
         def host_steps(c):
             for _ in range(c):
-                bw.step_host(hgn, hvn, hfn, DT, 1)    # H2D state, 1 step, D2H state, sync
+                if pipe is not None:
+                    pipe.step(hgn, hvn, hfn if model.nrows else None, DT, 1)
+                else:
+                    bw.step_host(hgn, hvn, hfn, DT, 1)    # H2D state, 1 step, D2H state, sync
         hep.step_fn = host_steps
         k_e2e = max(3, min(a.steps, 50))
         hep.advance(3)
@@ -334,10 +349,14 @@ def run_ours(a):
     if e2e:
         out["e2e"] = {"value": total_worlds/(e2e_ms*1e-3), "unit": "world-steps/s",
                       "h2d_bytes_per_step": e2e[1]*world_size, "d2h_bytes_per_step": e2e[2]*world_size,
-                      "steps": e2e[3], "how": "arb_step_host: pinned host state -> device, 1 step, "
-                                              "device -> host, synchronised, every step; same staggered "
-                                              "episodes as the timed region"}
-    if not a.no_cpu_baseline:
+                      "steps": e2e[3], "chunks": a.e2e_chunks,
+                      "how": ("HostPipeline.step (arb_step_host_strided on %d column blocks, one stream "
+                              "each): pinned host state -> device, 1 step, device -> host, all blocks "
+                              "synchronised, every step; same staggered episodes as the timed region"
+                              % a.e2e_chunks) if a.e2e_chunks > 1 else
+                             "arb_step_host: pinned host state -> device, 1 step, device -> host, "
+                             "synchronised, every step; same staggered episodes as the timed region"}
+    if not a.no_cpu_baseline and world_size == 1:      # rank 0 at N = 1 only
         out["cpu_baseline"] = cpu_baseline(scen, a.cpu_seconds)
     print(json.dumps(out))
     if world_size > 1:

@@ -160,6 +160,15 @@ int arb_step_end(arb_batch *batch, double dt);
 int arb_step_host(arb_batch *batch, double *h_gpos, double *h_gvel, double *h_cforce,
                   const double *dts, int nsteps);
 
+/* same for a SLICE of a larger host array: row e of the host arrays starts at h_x + e*host_ld
+ * (host_ld >= nworlds, in worlds), so that several batches -- each on its own stream -- can work on
+ * column blocks of one [elem][W_total] host state and overlap their copies with each other's
+ * kernels.  synchronize = 0: returns with the work enqueued; see arb_batch_synchronize. */
+int arb_step_host_strided(arb_batch *batch, double *h_gpos, double *h_gvel, double *h_cforce,
+                          int64_t host_ld, const double *dts, int nsteps, int synchronize);
+/* wait for everything enqueued on the batch's stream */
+int arb_batch_synchronize(arb_batch *batch);
+
 /* read-backs into DEVICE buffers, worlds [w0, w1), world-major: out[w-w0][...] */
 int arb_get_matrix(arb_batch *batch, int which, double *out, int64_t w0, int64_t w1);
 int arb_get_vector(arb_batch *batch, int which, double *out, int64_t w0, int64_t w1);

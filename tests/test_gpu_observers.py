@@ -102,3 +102,26 @@ def test_energy_monitor_matches_mass_matrix():
     assert np.abs(mon.kinetic_energy[0] - ec_ref).max() < 1e-10*np.abs(ec_ref).max()
     e = mon.mechanichal_energy
     assert np.abs(e[-1] - e[0]).max() < 2e-2*np.abs(e[0]).max()      # semi-implicit Euler, dt = 1 ms
+
+
+def test_host_pipeline_equals_device_step():
+    """HostPipeline (column blocks of pinned host state, one stream each, arb_step_host_strided)
+    gives bit for bit the states of the device-resident step, for a batch that does not split evenly."""
+    import torch
+    from arboris_b200 import scenarios
+    from arboris_b200.batch import BatchedWorld, HostPipeline
+    model = _world("human36_contact")
+    W = 1000
+    gp, gv = scenarios.initial_states(model, "human36_contact", 0, W)
+    bw = BatchedWorld(model, W, device="cuda:0")
+    bw.set_state(gp, gv)
+    hg = torch.as_tensor(gp).pin_memory()
+    hv = torch.as_tensor(gv).pin_memory()
+    hf = torch.zeros((model.nrows, W), dtype=torch.float64).pin_memory()
+    pipe = HostPipeline(model, W, chunks=7, device="cuda:0")
+    for _ in range(90):
+        pipe.step(hg.numpy(), hv.numpy(), hf.numpy(), 1e-3, 1)
+    bw.step(1e-3, 90)
+    g, v, f = bw.get_state()
+    assert np.array_equal(g, hg.numpy()) and np.array_equal(v, hv.numpy()) and np.array_equal(f, hf.numpy())
+    assert np.abs(f).max() > 0
