@@ -51,7 +51,12 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="human36_contact_262144", choices=sorted(WORKLOADS))
-    ap.add_argument("--worlds", type=int, default=0, help="override the total number of worlds")
+    ap.add_argument("--worlds", type=int, default=0, help="override the number of worlds (per GPU "
+                    "with --scaling weak, in total with --scaling strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): every GPU steps the workload's number of worlds (worlds are "
+                         "independent units: per-GPU work fixed, no collective); strong: the workload's "
+                         "worlds are split over the GPUs (BASELINE.json configs[4] read literally)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.)
@@ -195,6 +200,8 @@ def run_ours(a):
     scen, total = WORKLOADS[a.workload]
     if a.worlds:
         total = a.worlds
+    if a.scaling == "weak":
+        total *= world_size
     w0, w1 = shard_range(total, rank, world_size)   # contiguous block of worlds per GPU
     W = w1 - w0
     model = flatten(scenarios.BUILDERS[scen]())
@@ -315,7 +322,7 @@ def run_ours(a):
     out = {
         "metric": "world-steps/s (human36, fp64, dt=1ms)", "value": value, "unit": "world-steps/s",
         "n_gpus": world_size, "steps": a.steps, "warmup": warm, "ms_per_step": ms_all/a.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (seeded random initial states, SURVEY.md 8(d))",
         "config": {"workload": a.workload, "scenario": scen, "worlds_total": total_worlds,
                    "worlds_per_gpu": W, "dt": DT, "constraints": int(model.nc),
@@ -325,7 +332,11 @@ def run_ours(a):
                                "whole episode's mix of contact states" % (EPISODE, GROUPS, PHASE),
                    "l2": "state of all worlds (%.0f MB) and per-world scratch exceed L2; no flush needed"
                          % (W*STATE_BYTES_PER_WORLD_STEP/2/1e6),
-                   "parallelism": "worlds sharded over %d GPU(s), no collective on the step path" % world_size},
+                   "parallelism": "worlds sharded over %d GPU(s) (%s scaling: %s), no collective on the "
+                                  "step path" % (world_size, a.scaling,
+                                                 "every GPU holds the workload's number of worlds"
+                                                 if a.scaling == "weak" else
+                                                 "the workload's worlds are split over the GPUs")},
         "gpu_launches": int(launches),
         "nonfinite_worlds": int(nonfinite),
         "roofline": {"bound": "fp64", "achieved": achieved/1e12, "peak": fp64_peak/1e12,
@@ -382,12 +393,16 @@ def run_reference(a):
     if rank != 0:
         return
     scen, total = WORKLOADS[a.workload]
+    if a.worlds:
+        total = a.worlds
+    if a.scaling == "weak":
+        total *= max(a.gpus, 1)
     base = cpu_baseline(scen, a.cpu_seconds)
     v = base["value"]
     out = {
         "impl": "reference", "metric": "world-steps/s (human36, fp64, dt=1ms)", "value": v,
         "unit": "world-steps/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
-        "ms_per_step": 1e3/v if v else None, "higher_is_better": True, "scaling": "strong",
+        "ms_per_step": 1e3/v if v else None, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic (seeded random initial states)",
         "config": {"workload": a.workload, "scenario": scen, "worlds_total": total, "dt": DT},
         "cpu_baseline": base,
