@@ -195,6 +195,11 @@ def run_ours(a):
 
     rank, world_size, local = env_rank()
     torch.cuda.set_device(local)
+    # stdout carries exactly ONE line (the JSON, rank 0): anything a library prints there
+    # meanwhile (NCCL's version banner at the first collective) goes to stderr
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world_size > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     scen, total = WORKLOADS[a.workload]
@@ -228,10 +233,10 @@ def run_ours(a):
 
     ep.prime()                      # untimed: stagger the episodes
     warm = max(a.warmup, 3)
+    sampler = ClockSampler(local)   # samples cover the warm-up and the timed region (same load)
+    sampler.start()
     ep.advance(warm)
     barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     l0 = bw.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -240,6 +245,11 @@ def run_ours(a):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = bw.launch_count() - l0
+    if not sampler.rows:            # a very short timed region: keep the load up until one sample exists
+        t_end = time.time() + 10.
+        while not sampler.rows and time.time() < t_end:
+            ep.advance(PHASE)
+            torch.cuda.synchronize()
     sampler.stop_flag = True
     nonfinite = int((~torch.isfinite(bw.gvel)).any(0).sum())
 
@@ -369,7 +379,10 @@ def run_ours(a):
                              "synchronised, every step; same staggered episodes as the timed region"}
     if not a.no_cpu_baseline and world_size == 1:      # rank 0 at N = 1 only
         out["cpu_baseline"] = cpu_baseline(scen, a.cpu_seconds)
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(out), flush=True)
+    os.dup2(2, 1)
     if world_size > 1:
         dist.destroy_process_group()
 
