@@ -49,15 +49,24 @@ class BallAndSocketConstraint(Constraint):
 
 
 def choose_solver(shape0, shape1):
-    """Order the pair as the reference's ``collisions.choose_solver``
-    (collisions.py:14-65) does.  Only plane/point has a device solver so far;
-    the other pairs the reference supports are SURVEY.md section 8(f) row 3."""
+    """Order the pair and name the solver as the reference's
+    ``collisions.choose_solver`` (collisions.py:14-65) does.  The solvers themselves
+    are device code (``contact_collide`` in csrc/arb_constraints.cuh).  Box/Point is
+    refused: the reference names a ``box_point_collision`` that it never defines."""
     assert isinstance(shape0, Shape)
     assert isinstance(shape1, Shape)
-    if isinstance(shape0, Plane) and isinstance(shape1, Point):
-        return (shape0, shape1), 'plane_point_collision'
-    if isinstance(shape0, Point) and isinstance(shape1, Plane):
-        return (shape1, shape0), 'plane_point_collision'
+    table = {(Sphere, Sphere): (False, 'sphere_sphere_collision'),
+             (Sphere, Point): (False, 'sphere_point_collision'),
+             (Sphere, Plane): (True, 'plane_sphere_collision'),
+             (Sphere, Box): (True, 'box_sphere_collision'),
+             (Point, Sphere): (True, 'sphere_point_collision'),
+             (Point, Plane): (True, 'plane_point_collision'),
+             (Plane, Sphere): (False, 'plane_sphere_collision'),
+             (Plane, Point): (False, 'plane_point_collision'),
+             (Box, Sphere): (False, 'box_sphere_collision')}
+    for (c0, c1), (swap, solver) in table.items():
+        if type(shape0) is c0 and type(shape1) is c1:
+            return ((shape1, shape0) if swap else (shape0, shape1)), solver
     raise NotImplementedError()
 
 

@@ -26,6 +26,7 @@ JOINT_NGPOS = (16, 3, 2, 2, 2, 1, 1, 1, 3)
 CONS_JOINT_LIMITS, CONS_BALL_SOCKET, CONS_SOFT_FINGER = 0, 1, 2
 CONS_NDOL = (1, 3, 4)
 CTRL_WEIGHT, CTRL_PD = 0, 1
+PAIR_PLANE_SPHERE, PAIR_SPHERE_SPHERE, PAIR_BOX_SPHERE = 0, 1, 2   # arb_contact_pair
 CONS_NINT = 4
 CONS_NDBL = 48
 
@@ -177,17 +178,26 @@ def flatten(world):
             cons_dbl[k, 16:32] = H1.reshape(-1)
             cforce0.extend(np.asarray(c._force, dtype=float).reshape(-1)[:3])
         else:
-            s0, s1 = c._shapes
-            if _kind(s0, ("Plane",)) != 0 or _kind(s1, ("Point",)) != 0:
+            s0, s1 = c._shapes      # already ordered by choose_solver (collisions.py:14-65)
+            k0 = _kind(s0, ("Plane", "Sphere", "Box", "Point"))
+            k1 = _kind(s1, ("Sphere", "Point"))
+            pair = {0: PAIR_PLANE_SPHERE, 1: PAIR_SPHERE_SPHERE, 2: PAIR_BOX_SPHERE}.get(k0, -1)
+            if pair < 0 or k1 < 0:
                 raise NotImplementedError(
                     "contact pair %s/%s has no device collision solver"
                     % (type(s0).__name__, type(s1).__name__))
             b0, H0 = _frame_of(s0.frame, body_index)
             b1, H1 = _frame_of(s1.frame, body_index)
-            cons_int[k] = (b0, b1, 0, enabled)
+            cons_int[k] = (b0, b1, pair, enabled)
             cons_dbl[k, 0:16] = H0.reshape(-1)
             cons_dbl[k, 16:32] = H1.reshape(-1)
-            cons_dbl[k, 32:36] = np.asarray(s0.coeffs, dtype=float)
+            if pair == PAIR_PLANE_SPHERE:
+                cons_dbl[k, 32:36] = np.asarray(s0.coeffs, dtype=float)
+            elif pair == PAIR_BOX_SPHERE:
+                cons_dbl[k, 32:35] = np.asarray(s0.half_extents, dtype=float)
+            else:
+                cons_dbl[k, 41] = float(s0.radius)
+            cons_dbl[k, 42] = float(getattr(s1, "radius", 0.))
             cons_dbl[k, 36] = float(c._mu)
             cons_dbl[k, 37:40] = np.asarray(c._eps, dtype=float)
             cons_dbl[k, 40] = float(c._proximity)

@@ -31,11 +31,15 @@ class _Api(object):
             import arboris.core as core
             import arboris.constraints as constraints
             import arboris.controllers as controllers
+            import arboris.shapes as shapes
+            import arboris.joints as joints
+            import arboris.massmatrix as massmatrix
             from arboris.robots import human36, simplearm, snake, simpleshapes
         else:
-            from . import core, constraints, controllers
+            from . import core, constraints, controllers, shapes, joints, massmatrix
             from .robots import human36, simplearm, snake, simpleshapes
         self.core, self.constraints, self.controllers = core, constraints, controllers
+        self.shapes, self.joints, self.massmatrix = shapes, joints, massmatrix
         self.human36, self.simplearm, self.snake = human36, simplearm, snake
         self.simpleshapes = simpleshapes
 
@@ -134,6 +138,48 @@ def simplearm_limits_world(reference=False, shoulder=3.14/2 - 0.1):
     return w
 
 
+BALLS = (("BallA", .10, 1.0, (0., .13, 0.)), ("BallB", .12, 1.5, (.05, .38, .02)),
+         ("BallC", .08, 0.5, (.60, .31, .05)))          # name, radius, mass, start position
+BALLS_POINT = ("Needle", 0.2, (.61, .50, .04))                     # name, mass, start position
+
+
+def balls_world(reference=False):
+    """the collision pairs of collisions.py beyond plane/point.  Three
+    free balls and a free body carrying a Point fall on a ground plane and on a box fixed to
+    the ground: plane/sphere, plane/point, box/sphere, sphere/sphere, sphere/point contacts,
+    registered explicitly (``get_all_contacts`` would trip over the reference's undefined
+    ``box_point_collision``)."""
+    a = _Api(reference)
+    w = a.core.World()
+    a.simpleshapes.add_groundplane(w)
+    plane = list(w.itershapes())[0]
+    box = a.shapes.Box(a.core.SubFrame(w.ground, Hg.transl(.6, .1, 0.), 'BoxFrame'), (.2, .1, .2), 'Box')
+    w.register(box)
+    balls = []
+    for name, radius, mass, pos in BALLS:
+        body = a.core.Body(name=name, mass=a.massmatrix.sphere(radius, mass))
+        j = a.joints.FreeJoint(name=name + 'Joint')
+        w.add_link(w.ground, j, body)
+        j.gpos[:] = Hg.transl(*pos)
+        sh = a.shapes.Sphere(body, radius, name + 'Shape')
+        w.register(sh)
+        balls.append(sh)
+    name, mass, pos = BALLS_POINT
+    body = a.core.Body(name=name, mass=a.massmatrix.sphere(.05, mass))
+    j = a.joints.FreeJoint(name=name + 'Joint')
+    w.add_link(w.ground, j, body)
+    j.gpos[:] = Hg.transl(*pos)
+    tip = a.shapes.Point(a.core.SubFrame(body, Hg.transl(0., -.05, 0.), 'Tip'), 'TipShape')
+    w.register(tip)
+    w.register(a.controllers.WeightController())
+    A, B, C = balls
+    for s0, s1 in ((plane, A), (plane, B), (plane, C), (plane, tip), (box, C), (box, A),
+                   (A, B), (B, C), (C, tip), (tip, B)):
+        w.register(a.constraints.SoftFingerContact((s0, s1), .5))
+    w.init()
+    return w
+
+
 BUILDERS = {
     "simplearm": simplearm_world,
     "human36_free": human36_free_world,
@@ -141,6 +187,7 @@ BUILDERS = {
     "snake_loop": snake_loop_world,
     "ball_socket": ball_socket_world,
     "simplearm_limits": simplearm_limits_world,
+    "balls": balls_world,
 }
 
 
@@ -184,6 +231,14 @@ def initial_state(model, scenario, w):
         # corrected within one dt by BallAndSocketConstraint.solve and diverge
         gpos[lin] = SNAKE_QREF + rng.uniform(-1e-3, 1e-3, int(lin.sum()))
         gvel[:] = rng.uniform(-.2, .2, model.ndof)
+    elif scenario == "balls":
+        for j in free:
+            g = int(model.joint_gpos[j])
+            H0 = gpos[g:g + 16].reshape(4, 4)
+            t = rng.uniform(-.01, .01, 3)
+            r = rng.uniform(-.3, .3, 3)
+            gpos[g:g + 16] = np.dot(Hg.transl(*t), np.dot(H0, Hg.rotzyx(*r))).reshape(-1)
+        gvel[:] = rng.uniform(-.05, .05, model.ndof)
     elif scenario in ("simplearm", "ball_socket", "simplearm_limits"):
         if w > 0:
             gpos[lin] += rng.uniform(-0.2, 0.2, int(lin.sum()))

@@ -48,6 +48,95 @@ ARB_D void zaligned(const double* z, double* R, int* idx) {
   for (int i = 0; i < 3; ++i) { R[3 * i] = x[i]; R[3 * i + 1] = y[i]; R[3 * i + 2] = z[i]; }
 }
 
+// Collision solvers of the point contacts (collisions.py): shape 0 with frame Hg0 (world pose of
+// the shape frame), shape 1 with frame Hg1; cd = the constraint's parameters (arboris_b200.h).
+// Returns the signed distance and the two contact frames (same orientation zaligned(normal),
+// z along the contact normal), exactly as the reference composes them -- including its habit of
+// using plane-frame / box-frame coordinates of the normal as world coordinates.
+//   pair 0  _plane_sphere_collision   collisions.py:161-205  (Point = radius 0)
+//   pair 1  _sphere_sphere_collision  collisions.py:113-159  (Point = radius 0)
+//   pair 2  _box_sphere_collision     collisions.py:207-299  (argmin index work at :274)
+ARB_D double contact_collide(int pair, const double* cd, const Se3& Hg0, const Se3& Hg1, Se3& Hc0, Se3& Hc1,
+                             int* zidx) {
+  const double r0 = cd[41], r1 = cd[42];
+  double sdist;
+  if (pair == ARB_PAIR_SPHERE_SPHERE) {
+    double vec[3], nrm = 0.;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { vec[i] = Hg1.p[i] - Hg0.p[i]; nrm += vec[i] * vec[i]; }
+    nrm = sqrt(nrm);
+    sdist = nrm - r0 - r1;
+    double normal[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) normal[i] = vec[i] / nrm;
+    zaligned(normal, Hc0.R, zidx);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double z = Hc0.R[3 * i + 2];
+      Hc0.p[i] = Hg0.p[i] + r0 * z;
+      Hc1.p[i] = Hc0.p[i] + sdist * z;
+    }
+  } else {
+    Se3 Hg0i;
+    se3_inv(Hg0, Hg0i);
+    double p01[3], t3[3];
+    m3_mulv(Hg0i.R, Hg1.p, t3);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p01[i] = t3[i] + Hg0i.p[i];
+    if (pair == ARB_PAIR_BOX_SPHERE) {
+      const double* he = cd + 32;
+      double f0[3], fg[3], normal[3] = {0., 0., 0.};
+      const bool inside = fabs(p01[0]) <= he[0] && fabs(p01[1]) <= he[1] && fabs(p01[2]) <= he[2];
+      if (inside) {     // nearest face: argmin over (he - p, he + p), first minimum (numpy.argmin)
+        int im = 0;
+        double best = he[0] - p01[0];
+#pragma unroll
+        for (int i = 1; i < 6; ++i) {
+          const double v = i < 3 ? he[i] - p01[i] : he[i - 3] + p01[i - 3];
+          if (v < best) { best = v; im = i; }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) f0[i] = p01[i];
+        if (im < 3) { f0[im] = he[im]; normal[im] = 1.; }
+        else { f0[im - 3] = -he[im - 3]; normal[im - 3] = -1.; }
+        m3_mulv(Hg0.R, f0, fg);
+        double d2 = 0.;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { fg[i] += Hg0.p[i]; const double d = fg[i] - Hg1.p[i]; d2 += d * d; }
+        sdist = -sqrt(d2) - r1;
+      } else {          // nearest point of the box to the sphere centre
+#pragma unroll
+        for (int i = 0; i < 3; ++i) f0[i] = fmax(fmin(he[i], p01[i]), -he[i]);
+        m3_mulv(Hg0.R, f0, fg);
+        double vec[3], nrm = 0.;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { fg[i] += Hg0.p[i]; vec[i] = Hg1.p[i] - fg[i]; nrm += vec[i] * vec[i]; }
+        nrm = sqrt(nrm);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) normal[i] = vec[i] / nrm;
+        sdist = nrm - r1;
+      }
+      zaligned(normal, Hc0.R, zidx);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { Hc0.p[i] = fg[i]; Hc1.p[i] = Hg1.p[i] - r1 * normal[i]; }
+    } else {            // plane (coefficients in the plane's frame) against a sphere / point
+      const double* coef = cd + 32;
+      const double csdist = (coef[0] * p01[0] + coef[1] * p01[1] + coef[2] * p01[2]) - coef[3];
+      sdist = csdist - r1;
+      zaligned(coef, Hc0.R, zidx);
+      const double sg = sdist > 0. ? 1. : (sdist < 0. ? -1. : 0.);     // numpy.sign
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        Hc0.p[i] = p01[i] - csdist * coef[i];
+        Hc1.p[i] = p01[i] - (sg * r1) * coef[i];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Hc1.R[i] = Hc0.R[i];
+  return sdist;
+}
+
 // rows [r0, r0+nr) of  Ad(H_01) Ad(bpose1^-1) J_body1  -  Ad(bpose0^-1) J_body0  written to
 // the compacted constraint Jacobian starting at row `dol` (rows pre-zeroed).
 ARB_D void write_frame_pair_jac(const DevModel& m, const DevBatch& b, int64_t w, int b0, int b1,
@@ -228,31 +317,19 @@ ARB_D void world_update_constraints(const DevModel& m, const DevBatch& b, int64_
         for (int j = 0; j < n; ++j) AT(b.cjac, (L + r) * n + j) = 0.;
       write_frame_pair_jac(m, b, w, ci[0], ci[1], bp0, bp1, H01, 3, 3, L);
     } else {
-      // plane (shape frame bp0 on body b0) against point (frame bp1 on body b1)
-      Se3 bp0, bp1, P0, P1, Hg0, Hgp, Hg0i;
+      // shape 0 (frame bp0 on body b0) against shape 1 (frame bp1 on body b1)
+      Se3 bp0, bp1, P0, P1, Hg0, Hgp;
       se3_from_cdbl(cd, bp0);
       se3_from_cdbl(cd + 16, bp1);
-      const double* coef = cd + 32;
       load_pose(b, ci[0], w, P0);
       load_pose(b, ci[1], w, P1);
       se3_mul(P0, bp0, Hg0);
       se3_mul(P1, bp1, Hgp);
-      se3_inv(Hg0, Hg0i);
-      double p01[3], t3[3];
-      m3_mulv(Hg0i.R, Hgp.p, t3);
-#pragma unroll
-      for (int i = 0; i < 3; ++i) p01[i] = t3[i] + Hg0i.p[i];
-      const double csdist = (coef[0] * p01[0] + coef[1] * p01[1] + coef[2] * p01[2]) - coef[3];
-      const double sdist = csdist;  // radius 0
       Se3 Hc0, Hc1;
       int zi[3];
-      zaligned(coef, Hc0.R, zi);
+      const double sdist = contact_collide(ci[2], cd, Hg0, Hgp, Hc0, Hc1, zi);
 #pragma unroll
       for (int i = 0; i < 3; ++i) AT(b.czidx, 3 * c + i) = zi[i];
-#pragma unroll
-      for (int i = 0; i < 9; ++i) Hc1.R[i] = Hc0.R[i];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) { Hc0.p[i] = p01[i] - csdist * coef[i]; Hc1.p[i] = p01[i]; }
       // contact frames become subframes of their bodies (constraints.py:285-288)
       Se3 P0i, P1i, cb0, cb1, F0, F1, F0i, H01, Hc0i, Hc0c1;
       se3_inv(P0, P0i);

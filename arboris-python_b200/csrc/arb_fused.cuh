@@ -59,22 +59,11 @@ ARB_D bool constraint_update(const DevModel& m, int c, const Se3& P0, const Se3&
   if (type == ARB_CONS_BALL_SOCKET) {
     cb0 = bp0; cb1 = bp1; r0 = 3; nr = 3; active = true;
   } else {
-    Se3 Hg0, Hgp, Hg0i;
-    const double* coef = cd + 32;
+    Se3 Hg0, Hgp;
     se3_mul(P0, bp0, Hg0);
     se3_mul(P1, bp1, Hgp);
-    se3_inv(Hg0, Hg0i);
-    double p01[3], t3[3];
-    m3_mulv(Hg0i.R, Hgp.p, t3);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) p01[i] = t3[i] + Hg0i.p[i];
-    const double csdist = (coef[0] * p01[0] + coef[1] * p01[1] + coef[2] * p01[2]) - coef[3];
     Se3 Hc0, Hc1, P0i, P1i, Hc0i, Hc0c1;
-    zaligned(coef, Hc0.R, zidx);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) Hc1.R[i] = Hc0.R[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) { Hc0.p[i] = p01[i] - csdist * coef[i]; Hc1.p[i] = p01[i]; }
+    const double sdist = contact_collide(m.cint[ARB_CONS_NINT * c + 2], cd, Hg0, Hgp, Hc0, Hc1, zidx);
     se3_inv(P0, P0i);
     se3_inv(P1, P1i);
     se3_mul(P0i, Hc0, cb0);
@@ -86,8 +75,8 @@ ARB_D bool constraint_update(const DevModel& m, int c, const Se3& P0, const Se3&
     se3_mul(Hc0i, Hc1, Hc0c1);
     ad_apply(Hc0c1, f1t, y);
     const double dsdist = y[5] - f0t[5];
-    active = (csdist + dsdist * dt < cd[40]);
-    aux[0] = csdist;
+    active = (sdist + dsdist * dt < cd[40]);
+    aux[0] = sdist;
     r0 = 2; nr = 4;
     if (!active) return false;
     if (aligned) {

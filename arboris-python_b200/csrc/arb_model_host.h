@@ -116,6 +116,8 @@ static inline int build_host_model(const arb_model_desc* d, HostModel& m, std::s
       }
     } else if (ci[0] < 0 || ci[0] > nj || ci[1] < 0 || ci[1] > nj) {
       err = "constraint body index out of range"; return -3;
+    } else if (t == ARB_CONS_SOFT_FINGER_PLANE_POINT && (ci[2] < 0 || ci[2] > ARB_PAIR_BOX_SPHERE)) {
+      err = "unknown contact shape pair"; return -3;
     }
   }
   if (rows != m.nrows) { err = "nrows does not match the constraint list"; return -3; }
@@ -164,7 +166,8 @@ static inline int build_host_model(const arb_model_desc* d, HostModel& m, std::s
     for (int c = 0; c < m.nc && ok; ++c) {
       if (m.ctype[c] == ARB_CONS_JOINT_LIMITS) continue;
       if (m.cgen1[c] != 6 * g && m.cgen0[c] != 6 * g) continue;
-      if (m.ctype[c] != ARB_CONS_SOFT_FINGER_PLANE_POINT || m.cgen1[c] != 6 * g || m.cgen0[c] >= 0) { ok = false; break; }
+      if (m.ctype[c] != ARB_CONS_SOFT_FINGER_PLANE_POINT || m.cgen1[c] != 6 * g || m.cgen0[c] >= 0 ||
+          m.cint[ARB_CONS_NINT * c + 2] != ARB_PAIR_PLANE_SPHERE) { ok = false; break; }
       if (first < 0) first = c;
       for (int i = 0; i < 3; ++i)
         if (m.cdbl[ARB_CONS_NDBL * c + 32 + i] != m.cdbl[ARB_CONS_NDBL * first + 32 + i]) ok = false;

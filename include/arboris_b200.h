@@ -49,6 +49,13 @@ typedef enum {
 typedef enum {
   ARB_CONS_JOINT_LIMITS = 0, ARB_CONS_BALL_SOCKET = 1, ARB_CONS_SOFT_FINGER_PLANE_POINT = 2
 } arb_constraint_type;
+/* shape pair of a SoftFingerContact, ordered as collisions.choose_solver (collisions.py:14-65)
+ * orders it; a Point is a sphere of radius 0 */
+typedef enum {
+  ARB_PAIR_PLANE_SPHERE = 0,    /* plane_sphere_collision / plane_point_collision (:95-111) */
+  ARB_PAIR_SPHERE_SPHERE = 1,   /* sphere_sphere_collision / sphere_point_collision (:67-85) */
+  ARB_PAIR_BOX_SPHERE = 2       /* box_sphere_collision (:87-93) */
+} arb_contact_pair;
 
 /* controllers.py: WeightController:10, ProportionalDerivativeController:63 */
 typedef enum { ARB_CTRL_WEIGHT = 0, ARB_CTRL_PD = 1 } arb_controller_type;
@@ -61,9 +68,10 @@ typedef enum { ARB_CTRL_WEIGHT = 0, ARB_CTRL_PD = 1 } arb_controller_type;
  *  cons_int[c] / cons_dbl[c]:
  *   JOINT_LIMITS : int {joint, dof, gpos index, enabled}; dbl {min, max, proximity}
  *   BALL_SOCKET  : int {body0, body1, -, enabled}; dbl {bpose0[16], bpose1[16]}
- *   SOFT_FINGER  : int {plane body, point body, -, enabled};
- *                  dbl {plane frame bpose[16], point frame bpose[16],
- *                       plane coeffs[4] @32, mu @36, eps[3] @37, proximity @40}
+ *   SOFT_FINGER  : int {body of shape 0, body of shape 1, arb_contact_pair, enabled};
+ *                  dbl {shape 0 frame bpose[16], shape 1 frame bpose[16],
+ *                       plane coeffs[4] or box half extents[3] @32, mu @36, eps[3] @37,
+ *                       proximity @40, radius of shape 0 @41, radius of shape 1 @42}
  *  ctrl_int[a] / ctrl_dbl[a]:
  *   WEIGHT : dbl {gravity}
  *   PD     : int {m, blob offset}; blob {dof map[m], gpos map[m], kp[m*m],

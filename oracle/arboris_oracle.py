@@ -479,29 +479,68 @@ class OracleWorld(object):
             self.gforce += dot(cjac[c].T, f[r0:r0 + CONS_NDOL[self.ct[c]]])
 
     def _contact_update(self, c, dt):
-        """PointContact.update constraints.py:277-295 with the plane/point
-        collision solver collisions.py:105-111, 161-205 (radius 0) and
+        """PointContact.update constraints.py:277-295 with the collision solvers
+        collisions.py:67-111 (shape pair ordered by choose_solver :14-65) and
         SoftFingerContact.jacobian constraints.py:429-433."""
-        b0, b1 = int(self.ci[c][0]), int(self.ci[c][1])
+        b0, b1, pair = int(self.ci[c][0]), int(self.ci[c][1]), int(self.ci[c][2])
         d = self.cd[c]
-        bp0 = d[0:16].reshape(4, 4)     # plane shape frame on body b0
-        bp1 = d[16:32].reshape(4, 4)    # point shape frame on body b1
-        coeffs = d[32:36]
+        bp0 = d[0:16].reshape(4, 4)     # shape 0 frame on body b0
+        bp1 = d[16:32].reshape(4, 4)    # shape 1 frame on body b1
         prox = d[40]
+        radius0, radius1 = d[41], d[42]
         H_g0, _, _ = self._frame(b0, bp0)
         H_gp, _, _ = self._frame(b1, bp1)
         p_g1 = H_gp[0:3, 3]
-        # _plane_sphere_collision with radius1 = 0.
-        radius1 = 0.
-        normal = coeffs[0:3]
-        Hi = hinv(H_g0)
-        p_01 = dot(Hi[0:3, 0:3], p_g1) + Hi[0:3, 3]
-        csdist = dot(normal, p_01) - coeffs[3]
-        sdist = csdist - radius1
-        H_gc0, idx = zaligned(normal)
-        H_gc0[0:3, 3] = p_01 - csdist*normal
-        H_gc1 = H_gc0.copy()
-        H_gc1[0:3, 3] = p_01 - np.sign(sdist)*radius1*normal
+        if pair == 1:
+            # _sphere_sphere_collision collisions.py:150-159
+            p_g0 = H_g0[0:3, 3]
+            vec = p_g1 - p_g0
+            sdist = norm(vec) - radius0 - radius1
+            normal = vec/norm(vec)
+            H_gc0, idx = zaligned(normal)
+            z = H_gc0[0:3, 2]
+            H_gc0[0:3, 3] = p_g0 + radius0*z
+            H_gc1 = H_gc0.copy()
+            H_gc1[0:3, 3] += sdist*z
+        elif pair == 2:
+            # _box_sphere_collision collisions.py:268-299
+            half = d[32:35]
+            Hi = hinv(H_g0)
+            p_01 = dot(Hi[0:3, 0:3], p_g1) + Hi[0:3, 3]
+            if (abs(p_01) <= half).all():
+                i = int(np.argmin(np.hstack((half - p_01, half + p_01))))
+                f_0 = p_01.copy()
+                normal = zeros(3)
+                if i < 3:
+                    f_0[i] = half[i]
+                    normal[i] = 1
+                else:
+                    f_0[i - 3] = -half[i - 3]
+                    normal[i - 3] = -1
+                f_g = dot(H_g0[0:3, 0:3], f_0) + H_g0[0:3, 3]
+                sdist = -norm(f_g - p_g1) - radius1
+            else:
+                f_0 = np.maximum(np.minimum(half, p_01), -half)
+                f_g = dot(H_g0[0:3, 0:3], f_0) + H_g0[0:3, 3]
+                vec = p_g1 - f_g
+                normal = vec/norm(vec)
+                sdist = norm(vec) - radius1
+            H_gc0, idx = zaligned(normal)
+            H_gc1 = H_gc0.copy()
+            H_gc0[0:3, 3] = f_g
+            H_gc1[0:3, 3] = p_g1 - radius1*normal
+        else:
+            # _plane_sphere_collision collisions.py:193-205 (a Point has radius 0)
+            coeffs = d[32:36]
+            normal = coeffs[0:3]
+            Hi = hinv(H_g0)
+            p_01 = dot(Hi[0:3, 0:3], p_g1) + Hi[0:3, 3]
+            csdist = dot(normal, p_01) - coeffs[3]
+            sdist = csdist - radius1
+            H_gc0, idx = zaligned(normal)
+            H_gc0[0:3, 3] = p_01 - csdist*normal
+            H_gc1 = H_gc0.copy()
+            H_gc1[0:3, 3] = p_01 - np.sign(sdist)*radius1*normal
         # PointContact.update: contact frames become moving subframes of the bodies
         pose_b0 = self.pose[b0] if b0 > 0 else eye(4)
         pose_b1 = self.pose[b1] if b1 > 0 else eye(4)

@@ -206,7 +206,19 @@ def main():
     m, o = run_reference("simplearm_limits", [0, 1], 300, 1e-3, full_steps=(0,))
     save("simplearm_limits", m, o)
     print("  limits branches seen:", np.unique(o["branch"], return_counts=True))
+    balls()
+
+
+def balls():
+    """plane/sphere, box/sphere, sphere/sphere, sphere/point contacts."""
+    m, o = run_reference("balls", [0, 1, 2], 400, 1e-3, full_steps=(0,))
+    save("balls", m, o)
+    print("  balls: active per constraint:", o["active"].sum((0, 1)).tolist(),
+          "branches:", np.unique(o["branch"], return_counts=True))
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "balls":
+        balls()
+    else:
+        main()

@@ -11,7 +11,7 @@ from arboris_b200.shapes import Sphere, Plane, Point
 from arboris_b200.core import Joint, Constraint, NamedObjectsList
 
 ALL = ["simplearm", "human36_free", "human36_contact", "snake_loop", "ball_socket",
-       "simplearm_limits"]
+       "simplearm_limits", "balls"]
 
 
 @pytest.mark.parametrize("name", ALL)
@@ -107,7 +107,21 @@ def test_unknown_plugins_are_refused():
     w.add_link(w.ground, FreeJoint(), ball)
     w.register(Sphere(ball, 1.))
     w.register(Plane(w.ground))
-    assert get_all_contacts(w, friction_coeff=.5) == []      # sphere/plane has no device solver yet: skipped like NotImplementedError pairs
+    from arboris_b200.shapes import Box, Cylinder
+    w.register(Box(w.ground, (1., 1., 1.)))
+    w.register(Cylinder(w.ground, 1., 1.))
+    w.register(Point(ball))
+    # pairs without a collision solver are skipped like the reference's NotImplementedError pairs
+    # (collisions.py:35-64): here everything with the cylinder, and box/point, which the reference
+    # names but never defines; sphere/plane is ordered (plane, sphere) as choose_solver does
+    cs = get_all_contacts(w, friction_coeff=.5)
+    assert [(type(c._shapes[0]).__name__, type(c._shapes[1]).__name__) for c in cs] == \
+        [("Plane", "Sphere"), ("Box", "Sphere"), ("Plane", "Point")]
+    for c in cs:
+        w.register(c)
+    w.init()
+    m = flatten(w)
+    assert m.cons_int[:, 2].tolist() == [0, 2, 0] and m.cons_dbl[:, 42].tolist() == [1., 1., 0.]
 
 
 def test_replace_joint_and_gvel_views():
