@@ -168,7 +168,6 @@ extern "C" int arb_batch_set_option(arb_batch* b, const char* name, int value) {
   if (!b || !name) { arb_set_error("null argument"); return -1; }
   const std::string s(name);
   if (s == "force_phases") b->force_phases = value;
-  else if (s == "prepare_warp") b->prepare_warp = value;
   else if (s == "gs_coop") b->gs_coop = value;
   else if (s == "sort_period") b->sort_period = value < 0 ? 0 : value;
   else if (s == "time_stages") {

@@ -497,7 +497,6 @@ ARB_D int softfinger_solve_tiled(const double* v, const double* pA, const double
 template <int ND>
 ARB_D int gs_visit_one_body(const DevModel& m, const DevBatch& b, int64_t w, int c, double dt,
                             GsCache& k, int* status) {
-  const int type = m.ctype[c];
   const double* cd = m.cdbl + ARB_CONS_NDBL * c;
   const int r0 = m.crow[c];
   const bool side0 = m.cgen1[c] < 0;          // the moving body is body0: rows enter with a minus sign
@@ -760,8 +759,6 @@ ARB_D unsigned long long world_fused_gs(const DevModel& m, const DevBatch& b, in
       const int type = m.ctype[c];
       const int g1 = m.cgen1[c], g0 = m.cgen0[c];
       if (type == ARB_CONS_JOINT_LIMITS) {
-        const double* cd = m.cdbl + ARB_CONS_NDBL * c;
-        const int r0 = m.crow[c];
         if (k.g != g1) {
           gs_cache_flush(m, b, w, k);
           gs_cache_load<true>(m, b, w, k, g1, 1);
@@ -1063,7 +1060,6 @@ ARB_D unsigned long long world_fused_gs_coop(const DevModel& m, const DevBatch& 
 
 // ---------------------------------------------------------------------------------------
 ARB_D void world_fused_finish(const DevModel& m, const DevBatch& b, int64_t w, double dt) {
-  const int n = m.ndof;
   bool any = false;
   for (int c = 0; c < m.nc; ++c) any = any || FT(b.factive, c);
   // q'+ = q_free + Z^-1 G^T y

@@ -27,7 +27,6 @@ struct arb_batch {
   int* scratch_int = nullptr;
   int64_t launches = 0;
   int force_phases = 0;            // tests: run arb_step through the four phase kernels
-  int prepare_warp = 1;            // 0: lane-per-world prepare stage (tests, unsupported models)
   int gs_coop = 0;                 // 1: block-cooperative Gauss-Seidel kernel (pooled sliding solves) instead of the per-lane one
   int time_stages = 0;             // 1: CUDA events around every fused stage (diagnostic, synchronises per step)
   double stage_ms[4] = {0., 0., 0., 0.};   // accumulated prepare / gs / finish milliseconds, [3] = steps timed

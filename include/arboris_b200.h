@@ -136,11 +136,16 @@ int arb_batch_create(const arb_model *model, int64_t nworlds, int device, void *
                      arb_batch **out);
 void arb_batch_destroy(arb_batch *batch);
 int arb_batch_set_stream(arb_batch *batch, void *stream);
-/* tuning/testing switches: "force_phases" (1: arb_step runs the four API phase kernels
- * instead of the fused stages), "gs_coop" (1: block-cooperative Gauss-Seidel kernel, sliding solves pooled
- * through shared memory, instead of the per-lane one; bit-identical results), "time_stages" (1: CUDA events around every fused stage,
- * synchronising after every step -- a diagnostic for bench.py, read with arb_batch_stage_ms;
- * setting it clears the accumulators) */
+/* tuning/testing switches:
+ *  "force_phases" 1: arb_step runs the four API phase kernels instead of the fused stages;
+ *  "sort_period"  N: the fused step re-assigns the worlds to threads by contact state every N
+ *                 steps (default 2; 0: never, worlds stay in arrival order); results are
+ *                 bit-identical whatever the value;
+ *  "gs_coop"      1: block-cooperative Gauss-Seidel kernel (sliding solves pooled through
+ *                 shared memory) instead of the per-lane one; bit-identical results;
+ *  "time_stages"  1: CUDA events around every fused stage, synchronising after every step -- a
+ *                 diagnostic for bench.py, read with arb_batch_stage_ms; setting it clears the
+ *                 accumulators */
 int arb_batch_set_option(arb_batch *batch, const char *name, int value);
 
 /* caller-owned DEVICE state, layouts in the header comment */
