@@ -180,6 +180,52 @@ def balls_world(reference=False):
     return w
 
 
+def zoo_world(reference=False):
+    """what the three benchmark robots do not exercise.  Two
+    simplearms side by side (name prefixes), and a chain that goes through every other stock
+    joint type -- TxTyTz, RzRx, RyRx, RzRy, RzRyRx, Ry, Rx -- with joint frames that are
+    SubFrames on both sides (H_pr, H_cn != I), bodies with viscosity, one massless body, a
+    two ProportionalDerivativeControllers with diagonal gains on five of the dofs and JointLimits
+    on a hinge."""
+    a = _Api(reference)
+    w = a.core.World()
+    a.simplearm.add_simplearm(w, name='Left')
+    a.simplearm.add_simplearm(w, name='Right', lengths=(.4, .3, .1), masses=(.7, .5, .1))
+    J, mm = a.joints, a.massmatrix
+    specs = (('Slider', J.TxTyTzJoint, mm.box((.1, .2, .15), 2.)),
+             ('RzRx', J.RzRxJoint, mm.ellipsoid((.1, .05, .2), 1.2)),
+             ('RyRx', J.RyRxJoint, mm.cylinder(.3, .05, .8)),
+             ('RzRy', J.RzRyJoint, None),
+             ('Ball', J.RzRyRxJoint, mm.sphere(.1, 1.1)),
+             ('Ry', J.RyJoint, mm.box((.05, .1, .05), .4)),
+             ('Rx', J.RxJoint, mm.sphere(.05, .3)))
+    parent = w.ground
+    joints = {}
+    for i, (name, cls, mass) in enumerate(specs):
+        visc = np.diag([.02, .03, .01, .2, .1, .3])*(i % 3 == 0)
+        body = a.core.Body(name=name + 'Body', mass=mass, viscosity=visc if visc.any() else None)
+        H0 = np.dot(Hg.transl(.1 + .05*i, .2, -.03*i), Hg.rotzyx(.2*i, -.1, .3))
+        H1 = np.dot(Hg.transl(0., -.05*i, .02), Hg.rotzyx(.1, .15*i, -.2))
+        f0 = a.core.SubFrame(parent, H0, name + 'Base')
+        f1 = a.core.SubFrame(body, H1, name + 'Tip') if i % 2 == 0 else body
+        j = cls(name=name)
+        w.add_link(f0, j, f1)
+        joints[name] = j
+        parent = body
+    w.register(a.controllers.WeightController())
+    w.init()      # the reference's PD controller reads joint.dof in its constructor
+    # (the reference's PD controller stacks joint.gpos with array(): joints of equal ndof only)
+    w.register(a.controllers.ProportionalDerivativeController(
+        [joints['Slider']], kp=np.diag([30., 20., 25.]), kd=np.diag([3., 2., 2.5]),
+        gpos_des=[.1, -.05, .02], gvel_des=[0., .1, 0.]))
+    w.register(a.controllers.ProportionalDerivativeController(
+        [joints['Ry'], joints['Rx']], kp=np.diag([4., 20.]), kd=np.diag([.4, .5]),
+        gpos_des=[.3, .8], gvel_des=[-.2, 0.]))     # drives the Rx hinge into its limit
+    w.register(a.constraints.JointLimits(joints['Rx'], -.4, .4))
+    w.init()
+    return w
+
+
 BUILDERS = {
     "simplearm": simplearm_world,
     "human36_free": human36_free_world,
@@ -188,6 +234,7 @@ BUILDERS = {
     "ball_socket": ball_socket_world,
     "simplearm_limits": simplearm_limits_world,
     "balls": balls_world,
+    "zoo": zoo_world,
 }
 
 
@@ -239,6 +286,9 @@ def initial_state(model, scenario, w):
             r = rng.uniform(-.3, .3, 3)
             gpos[g:g + 16] = np.dot(Hg.transl(*t), np.dot(H0, Hg.rotzyx(*r))).reshape(-1)
         gvel[:] = rng.uniform(-.05, .05, model.ndof)
+    elif scenario == "zoo":
+        gpos[lin] = rng.uniform(-.3, .3, int(lin.sum()))
+        gvel[:] = rng.uniform(-.5, .5, model.ndof)
     elif scenario in ("simplearm", "ball_socket", "simplearm_limits"):
         if w > 0:
             gpos[lin] += rng.uniform(-0.2, 0.2, int(lin.sum()))

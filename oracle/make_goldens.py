@@ -207,6 +207,16 @@ def main():
     save("simplearm_limits", m, o)
     print("  limits branches seen:", np.unique(o["branch"], return_counts=True))
     balls()
+    zoo()
+
+
+def zoo():
+    """every stock joint type, SubFrame joint frames, viscosity, two
+    robots in one world, PD controller (diagonal gains), joint limits."""
+    m, o = run_reference("zoo", [0, 1, 2], 300, 1e-3, full_steps=(0, 1, 150))
+    save("zoo", m, o)
+    print("  zoo: limit active in", int(o["active"].sum()), "world-steps; branches",
+          np.unique(o["branch"], return_counts=True))
 
 
 def balls():
@@ -218,7 +228,7 @@ def balls():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "balls":
-        balls()
+    if len(sys.argv) > 1 and sys.argv[1] in ("balls", "zoo"):
+        {"balls": balls, "zoo": zoo}[sys.argv[1]]()
     else:
         main()

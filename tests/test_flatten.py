@@ -11,7 +11,7 @@ from arboris_b200.shapes import Sphere, Plane, Point
 from arboris_b200.core import Joint, Constraint, NamedObjectsList
 
 ALL = ["simplearm", "human36_free", "human36_contact", "snake_loop", "ball_socket",
-       "simplearm_limits", "balls"]
+       "simplearm_limits", "balls", "zoo"]
 
 
 @pytest.mark.parametrize("name", ALL)

@@ -32,7 +32,7 @@ def _batch(model, W):
 
 
 @pytest.mark.parametrize("name", ["simplearm", "human36_free", "ball_socket",
-                                  "simplearm_limits", "snake_loop", "human36_contact", "balls"])
+                                  "simplearm_limits", "snake_loop", "human36_contact", "balls", "zoo"])
 def test_phases_vs_real_reference(torch_cuda, name):
     model, tr = load_golden(name)
     n, dt = model.ndof, float(tr["dt"])
@@ -73,7 +73,7 @@ def test_phases_vs_real_reference(torch_cuda, name):
 
 
 @pytest.mark.parametrize("name", ["simplearm", "human36_free", "ball_socket",
-                                  "simplearm_limits", "snake_loop", "human36_contact", "balls"])
+                                  "simplearm_limits", "snake_loop", "human36_contact", "balls", "zoo"])
 def test_fused_step_vs_real_reference(torch_cuda, name):
     """arb_step (the fused path) from the reference's state at every step."""
     model, tr = load_golden(name)

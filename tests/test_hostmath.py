@@ -22,7 +22,7 @@ def rel(a, b):
 
 @pytest.mark.parametrize("name,tol", [("simplearm", 1e-12), ("human36_free", 1e-10),
                                       ("ball_socket", 1e-12), ("simplearm_limits", 1e-12),
-                                      ("snake_loop", 1e-10), ("human36_contact", 1e-10), ("balls", 1e-10)])
+                                      ("snake_loop", 1e-10), ("human36_contact", 1e-10), ("balls", 1e-10), ("zoo", 1e-10)])
 def test_world_routines_vs_real_reference(name, tol):
     """per step from identical states: M, N, Z, Y, forces, velocities <= tol relative;
     active sets and solver branches bit-exact."""
@@ -130,7 +130,7 @@ def test_solve4_and_exp():
 
 @pytest.mark.parametrize("name,tol", [("simplearm", 1e-12), ("human36_free", 1e-10),
                                       ("ball_socket", 1e-12), ("simplearm_limits", 1e-12),
-                                      ("snake_loop", 1e-10), ("human36_contact", 1e-10), ("balls", 1e-10)])
+                                      ("snake_loop", 1e-10), ("human36_contact", 1e-10), ("balls", 1e-10), ("zoo", 1e-10)])
 @pytest.mark.parametrize("coop", [1, 0])
 def test_fused_algorithm_vs_real_reference(name, tol, coop):
     """The fused step's algorithm in scalar form (no-fill tree factorisation of Z instead of

@@ -158,7 +158,7 @@ def _teacher_forced(name, stepper_factory, tol):
 
 
 @pytest.mark.parametrize("name", ["simplearm", "human36_free", "ball_socket",
-                                  "simplearm_limits", "snake_loop", "human36_contact", "balls"])
+                                  "simplearm_limits", "snake_loop", "human36_contact", "balls", "zoo"])
 def test_oracle_matches_real_reference(name):
     """The restatement reproduces the real reference bit-for-bit (same numpy calls)."""
     _teacher_forced(name, lambda m: OracleWorld(m.to_dict()), 1e-13)
