@@ -333,8 +333,19 @@ class HostPipeline(object):
     def __init__(self, world_or_model, nworlds, chunks=8, device=None):
         from .shard import shard_range
         self.nworlds = int(nworlds)
-        chunks = max(1, min(int(chunks), (self.nworlds + 31)//32))
-        self.ranges = [shard_range(self.nworlds, k, chunks) for k in range(chunks)]
+        if isinstance(chunks, (list, tuple)):
+            # relative sizes of the blocks, e.g. (1, 3, 4, 4, 3, 1): small first and last blocks
+            # shorten the exposed first copy-in / last copy-out, large middle blocks keep the
+            # kernels efficient
+            tot = float(sum(chunks))
+            edges = [0]
+            for c in chunks:
+                edges.append(min(self.nworlds, max(edges[-1], int(round(self.nworlds*sum(chunks[:len(edges)])/tot/32.))*32)))
+            edges[-1] = self.nworlds
+            self.ranges = list(zip(edges[:-1], edges[1:]))
+        else:
+            chunks = max(1, min(int(chunks), (self.nworlds + 31)//32))
+            self.ranges = [shard_range(self.nworlds, k, chunks) for k in range(chunks)]
         self.ranges = [r for r in self.ranges if r[1] > r[0]]
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         first = BatchedWorld(world_or_model, self.ranges[0][1] - self.ranges[0][0], device=dev,

@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.)
-    ap.add_argument("--e2e-chunks", type=int, default=8,
+    ap.add_argument("--e2e-chunks", type=lambda t: [int(x) for x in t.split(",")] if "," in t else int(t), default=8,
                     help="column blocks (each on its own stream) of the end-to-end pass; 1 = one "
                          "synchronous arb_step_host call per step")
     ap.add_argument("--opt", action="append", help="arb_batch_set_option switch, name=value (A/B runs)")
@@ -274,7 +274,7 @@ def run_ours(a):
         hep.state, hep.init = (hg, hv, hf), (torch.as_tensor(gp), torch.as_tensor(gv), None)
 
         pipe = None
-        if a.e2e_chunks > 1:
+        if isinstance(a.e2e_chunks, list) or a.e2e_chunks > 1:
             # the public end-to-end call: column blocks of the host state, one stream each, so
             # that copies and kernels of different blocks overlap (batch.HostPipeline)
             pipe = HostPipeline(model, W, chunks=a.e2e_chunks, device=bw.device)
@@ -374,7 +374,8 @@ def run_ours(a):
                       "how": ("HostPipeline.step (arb_step_host_strided on %d column blocks, one stream "
                               "each): pinned host state -> device, 1 step, device -> host, all blocks "
                               "synchronised, every step; same staggered episodes as the timed region"
-                              % a.e2e_chunks) if a.e2e_chunks > 1 else
+                              % (len(a.e2e_chunks) if isinstance(a.e2e_chunks, list) else a.e2e_chunks))
+                             if (isinstance(a.e2e_chunks, list) or a.e2e_chunks > 1) else
                              "arb_step_host: pinned host state -> device, 1 step, device -> host, "
                              "synchronised, every step; same staggered episodes as the timed region"}
     if not a.no_cpu_baseline and world_size == 1:      # rank 0 at N = 1 only
