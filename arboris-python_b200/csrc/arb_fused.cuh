@@ -749,34 +749,35 @@ ARB_D unsigned long long world_fused_gs(const DevModel& m, const DevBatch& b, in
 #ifndef ARB_X_SWEEPS
 #define ARB_X_SWEEPS ARB_GS_SWEEPS   /* timing experiments only */
 #endif
-  for (int sweep = 0; sweep < ARB_X_SWEEPS; ++sweep) {
-    for (int c = 0; c < m.nc; ++c) {
-      const bool act = c < 32 ? ((amask >> c) & 1u) != 0u : FT(b.factive, c) != 0;
-      // Block switches are decided per WARP: every lane still in the loop follows the same
-      // sequence of cached blocks, so the flush/load code runs once per switch, not once per
-      // subset of lanes.  (A lane whose constraint c is inactive just skips the visit.)
-      if (!arb_warp_any(act)) continue;
-      const int type = m.ctype[c];
-      const int g1 = m.cgen1[c], g0 = m.cgen0[c];
-      if (type == ARB_CONS_JOINT_LIMITS) {
-        if (k.g != g1) {
-          gs_cache_flush(m, b, w, k);
-          gs_cache_load<true>(m, b, w, k, g1, 1);
-        }
-        if (act) gs_visit_limit(m, b, c, dt, k);
-        continue;
-      }
-      if (g1 >= 0 && g0 >= 0) {
-        gs_cache_flush(m, b, w, k);
-        if (act) gs_visit_two_body(m, b, w, c, dt, &status);
-        continue;
-      }
-      const int gF = g1 < 0 ? g0 : g1;
-      if (k.g != gF) {
-        gs_cache_flush(m, b, w, k);
-        gs_cache_load<true>(m, b, w, k, gF, 6);
-      }
-      if (!act) continue;
+  // One walk over (sweep, constraint) pairs plus a final pseudo-visit that only flushes: the
+  // block-switch code (flush + load, ~2.5 KB of SASS) exists ONCE -- the sweep loop has to fit
+  // the 32 KB instruction cache of the SM together with the sliding solve.
+  const int nvis = ARB_X_SWEEPS * m.nc;
+  for (int v = 0, c = 0, sweep = 0; v <= nvis; ++v, ++c) {
+    if (c == m.nc) { c = 0; ++sweep; }
+    const bool last = v == nvis;
+    const bool act = !last && (c < 32 ? ((amask >> c) & 1u) != 0u : FT(b.factive, c) != 0);
+    // Block switches are decided per WARP: every lane still in the loop follows the same
+    // sequence of cached blocks, so the flush/load code runs once per switch, not once per
+    // subset of lanes.  (A lane whose constraint c is inactive just skips the visit.)
+    if (!last && !arb_warp_any(act)) continue;
+    const int type = last ? -1 : m.ctype[c];
+    const int g1 = last ? -1 : m.cgen1[c], g0 = last ? -1 : m.cgen0[c];
+    // the block this visit needs in the cache: a limited dof (1 row), the moving body of a
+    // one-body constraint (6 rows), or none (two-body constraints go through memory; the end)
+    int gneed = -1, nneed = 0;
+    if (type == ARB_CONS_JOINT_LIMITS) { gneed = g1; nneed = 1; }
+    else if (!last && !(g1 >= 0 && g0 >= 0)) { gneed = g1 < 0 ? g0 : g1; nneed = 6; }
+    if (k.g != gneed) {
+      gs_cache_flush(m, b, w, k);
+      if (gneed >= 0) gs_cache_load<true>(m, b, w, k, gneed, nneed);
+    }
+    if (!act) continue;
+    if (type == ARB_CONS_JOINT_LIMITS) {
+      gs_visit_limit(m, b, c, dt, k);
+    } else if (gneed < 0) {
+      gs_visit_two_body(m, b, w, c, dt, &status);
+    } else {
       if (c + 1 < m.nc) gs_prefetch_visit(m, b, c + 1);
       if (type == ARB_CONS_BALL_SOCKET) gs_visit_one_body<3>(m, b, w, c, dt, k, &status);
       else if (gs_visit_one_body<4>(m, b, w, c, dt, k, &status) == 3 && c < 32) slid |= 1u << c;
@@ -785,7 +786,6 @@ ARB_D unsigned long long world_fused_gs(const DevModel& m, const DevBatch& b, in
 #endif
     }
   }
-  gs_cache_flush(m, b, w, k);
   for (int r = 0; r < m.nrows; ++r) ST(b.cforce, r) = FT(b.ff, r);
   if (status) b.status[w] |= status;
   return gs_sort_key(m, slid, amask);
