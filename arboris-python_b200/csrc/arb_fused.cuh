@@ -280,19 +280,48 @@ ARB_D void gs_cache_flush(const DevModel& m, const DevBatch& b, int64_t w, GsCac
     double* py = b.fy + k.g * ARB_TILE;
     const double* pl = b.fLam + k.g * ARB_TILE;        // Lambda[r, g + p] = pl[(r NG + p) TILE]
     const int rowstride = NG * ARB_TILE;
+    // Rows outside the block, four at a time: the loads of four rows are in flight together
+    // (the switch is bound by memory latency), and the loop is NOT unrolled further -- this code
+    // sits in the sweep loop, whose instructions must fit the SM's 32 KB instruction cache
+    // together with the sliding solve.  Row i of the outside rows is i (< g) or i + n.
+    const int nout = NG - k.n;
     if (k.n == 6) {
-      for (int r = 0; r < NG; ++r, pl += rowstride) {
-        if (r >= k.g && r < k.g + 6) continue;
-        double acc = 0.;
+#pragma unroll 1
+      for (int i0 = 0; i0 < nout; i0 += 4) {
+        double acc[4];
+        int rr[4];
 #pragma unroll
-        for (int p = 0; p < 6; ++p) acc += pl[p * ARB_TILE] * k.dy[p];
-        b.fu[r * ARB_TILE] += acc;
+        for (int i = 0; i < 4; ++i) {
+          const int ii = i0 + i < nout ? i0 + i : nout - 1;
+          rr[i] = ii < k.g ? ii : ii + 6;
+          const double* q = pl + rr[i] * rowstride;
+          double a = 0.;
+#pragma unroll
+          for (int p = 0; p < 6; ++p) a += q[p * ARB_TILE] * k.dy[p];
+          acc[i] = a;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i0 + i < nout) b.fu[rr[i] * ARB_TILE] += acc[i];
       }
 #pragma unroll
       for (int p = 0; p < 6; ++p) py[p * ARB_TILE] += k.dy[p];
     } else {
-      for (int r = 0; r < NG; ++r, pl += rowstride)
-        if (r != k.g) b.fu[r * ARB_TILE] += pl[0] * k.dy[0];
+#pragma unroll 1
+      for (int i0 = 0; i0 < nout; i0 += 4) {
+        double lam[4], uu[4];
+        int rr[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int ii = i0 + i < nout ? i0 + i : nout - 1;
+          rr[i] = ii < k.g ? ii : ii + 1;
+          lam[i] = pl[rr[i] * rowstride];
+          uu[i] = b.fu[rr[i] * ARB_TILE];
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i0 + i < nout) b.fu[rr[i] * ARB_TILE] = uu[i] + lam[i] * k.dy[0];
+      }
       py[0] += k.dy[0];
     }
   }
@@ -323,13 +352,11 @@ ARB_D void gs_cache_load(const DevModel& m, const DevBatch& b, int64_t w, GsCach
       for (int q = 0; q < 6; ++q) GSL(k, 6 * p + q) = pl[q * ARB_TILE];
       pl += rowstride;
     }
-  } else {
+  } else {      // a 1-row block only ever uses element 0 of L, u and dy
 #pragma unroll
-    for (int i = 0; i < 36; ++i) GSL(k, i) = 0.;
-#pragma unroll
-    for (int p = 0; p < 6; ++p) k.u[p] = 0.;
+    for (int p = 1; p < 6; ++p) k.u[p] = 0.;
     GSL(k, 0) = pl[0];
-    if (WITH_U) k.u[0] = pu[0];
+    k.u[0] = WITH_U ? pu[0] : 0.;
   }
 }
 
