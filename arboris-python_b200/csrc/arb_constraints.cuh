@@ -169,6 +169,19 @@ ARB_D void write_frame_pair_jac(const DevModel& m, const DevBatch& b, int64_t w,
   }
 }
 
+// general solve of the sliding branch: pivoted LU of the 4x4 system (out of line: rare)
+ARB_NOINLINE void softfinger_sliding_lu(const double* A, const double* alpha, double s, const double* eps,
+                                        double* newf, int* status) {
+  double A2[16], nalpha[4];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) A2[i] = A[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) A2[5 * i] -= s * (1. / (eps[i] * eps[i]));
+#pragma unroll
+  for (int i = 0; i < 4; ++i) nalpha[i] = -alpha[i];
+  if (!solve_small<4>(A2, nalpha, newf)) *status |= ARB_STATUS_SINGULAR;
+}
+
 // Sliding branch of SoftFingerContact.solve (constraints.py:803-836): s = smallest real
 // eigenvalue <= 0 of B (with the reference's scalar inner products), then
 // newf = (A - s diag(eps^-2, 0))^-1 (-alpha).
@@ -217,14 +230,35 @@ ARB_NOINLINE void softfinger_sliding(const double* A, const double* alpha, doubl
   }
   if (!found) { s = -1e10; *status |= ARB_STATUS_EIG_NOROOT; }
   if (s < -1e10) s = -1e10;
-  double A2[16], nalpha[4];
+  // newf = (A - s diag(eps^-2, 0))^-1 (-alpha)        (numpy.linalg.solve, constraints.py:834)
+  // by elimination of the normal row (its pivot y_n = A[3][3] > 0 is the normal admittance) and
+  // Cramer's rule on the 3x3 Schur complement -- a third of the code of the pivoted 4x4 LU, which
+  // matters in the sweep loop (instruction cache); the LU is the fallback when the complement
+  // is badly scaled.
+  double B[9];
+  const double idn = 1. / A[15];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) A2[i] = A[i];
+  for (int i = 0; i < 3; ++i)
 #pragma unroll
-  for (int i = 0; i < 3; ++i) A2[5 * i] -= s * (1. / (eps[i] * eps[i]));
-#pragma unroll
-  for (int i = 0; i < 4; ++i) nalpha[i] = -alpha[i];
-  if (!solve_small<4>(A2, nalpha, newf)) *status |= ARB_STATUS_SINGULAR;
+    for (int j = 0; j < 3; ++j)
+      B[3 * i + j] = (A[4 * i + j] - ((i == j) ? s * (1. / (eps[i] * eps[i])) : 0.)) - (A[4 * i + 3] * idn) * A[12 + j];
+  const double rhs[3] = {-alpha[0] + (A[3] * idn) * alpha[3], -alpha[1] + (A[7] * idn) * alpha[3],
+                         -alpha[2] + (A[11] * idn) * alpha[3]};
+  const double c00 = B[4] * B[8] - B[5] * B[7], c01 = B[5] * B[6] - B[3] * B[8], c02 = B[3] * B[7] - B[4] * B[6];
+  const double det = B[0] * c00 + B[1] * c01 + B[2] * c02;
+  const double scale = (fabs(B[0]) + fabs(B[4]) + fabs(B[8])) * (1. / 3.);
+  if (fabs(det) > 1e-9 * scale * scale * scale && fabs(A[15]) > 0.) {
+    const double c10 = B[2] * B[7] - B[1] * B[8], c11 = B[0] * B[8] - B[2] * B[6], c12 = B[1] * B[6] - B[0] * B[7];
+    const double c20 = B[1] * B[5] - B[2] * B[4], c21 = B[2] * B[3] - B[0] * B[5], c22 = B[0] * B[4] - B[1] * B[3];
+    const double id = 1. / det;
+    // x = adj(B) rhs / det,  adj(B)_ij = cofactor_ji
+    newf[0] = (c00 * rhs[0] + c10 * rhs[1] + c20 * rhs[2]) * id;
+    newf[1] = (c01 * rhs[0] + c11 * rhs[1] + c21 * rhs[2]) * id;
+    newf[2] = (c02 * rhs[0] + c12 * rhs[1] + c22 * rhs[2]) * id;
+    newf[3] = (-alpha[3] - (A[12] * newf[0] + A[13] * newf[1] + A[14] * newf[2])) * idn;
+  } else {
+    softfinger_sliding_lu(A, alpha, s, eps, newf, status);
+  }
 }
 
 // SoftFingerContact.solve (constraints.py:780-836).  v: constraint velocity (4),
