@@ -409,11 +409,49 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
 }
 
 // ---------------------------------------------------------------------------------------
+// The root-to-leaf passes below visit the joints in depth-first order, so most joints hang on the
+// body of the joint visited just before: its (V, V^) are still in registers (`prev`).  A body's
+// values go through aV only when another child reads them later, or when the generator rows read
+// them (fused_gen_rows).
+ARB_D bool artic_child_reads_aV(const DevModel& m, int j, int next, bool marked_only) {
+  for (int c = m.jchild0[j]; c >= 0; c = m.jsib[c])
+    if (c != next && (!marked_only || m.jmark[c])) return true;
+  return false;
+}
+ARB_D bool artic_is_gen_body(const DevModel& m, int j) {
+  for (int g = 0; g < m.ngen; ++g)
+    if (m.gen_body[g] == j + 1) return true;
+  return false;
+}
+// (V, V^) of the child: X applied in place
+ARB_D void artic_down(const Se3& X, double* V, double* Vh) {
+  double a[6], c[6];
+  iad_apply(X, V, a);
+  iad_apply(X, Vh, c);
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { V[i] = a[i]; Vh[i] = c[i]; }
+}
+
+// ---------------------------------------------------------------------------------------
 // root-to-leaf pass for ONE right-hand side over ALL joints:  x_k = u_k - LA_k V - LM_k Vh.
 // u_k is read from `u` for marked joints (or all joints if !marked_u), else 0.  x is written
-// to `x`; (V, Vh) of every body with children is kept in aV[j][0..11].
-template <bool MARKED_U>
-ARB_D void artic_forward_full(const DevModel& m, const DevBatch& b, int64_t w, const double* u, double* x) {
+// to `x`; (V, Vh) of the bodies other passes read is kept in aV[j][0..11].
+// NE "extra" right-hand sides ride along over the marked joints when `ext` is set (the rows
+// LA, LM, s, s^ are read once for all of them): unit generalized forces on the dofs ek[e], whose
+// reduced right-hand sides artic_backward_generators left in au[1 + e]; solutions to ax[e],
+// (V, Vh) to aV[j][12 (1 + e) ..].
+template <bool MARKED_U, int NE>
+ARB_D void artic_forward_full(const DevModel& m, const DevBatch& b, int64_t w, const double* u, double* x,
+                              bool ext = false, const int* ek = nullptr) {
+  const int n = m.ndof;
+  double V[1 + NE][6], Vh[1 + NE][6];
+  int eoff[NE > 0 ? NE : 1], ekc[NE > 0 ? NE : 1];
+#pragma unroll
+  for (int e = 0; e < NE; ++e) {
+    eoff[e] = ext ? m.coloff[m.dofbody[ek[e]]] : 0;
+    ekc[e] = ext ? m.dofpos[ek[e]] + 1 : 0;
+  }
+  int prev = -2;
   for (int j = 0; j < m.nj; ++j) {
     if (j + 1 < m.nj) {
       arb_prefetch_rows<12>(b.aX + (j + 1) * (12 * ARB_TILE));
@@ -422,48 +460,92 @@ ARB_D void artic_forward_full(const DevModel& m, const DevBatch& b, int64_t w, c
     const int par = m.jparent[j];
     const int nd = arb_joint_ndof(m.jtype[j]);
     const int dof = m.jdof[j];
-    double V[6], Vh[6];
+    const bool ex = NE > 0 && ext && m.jmark[j];
     if (par == 0) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { V[i] = 0.; Vh[i] = 0.; }
+      for (int r = 0; r < 1 + NE; ++r)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { V[r][i] = 0.; Vh[r][i] = 0.; }
     } else {
       Se3 X;
       load_se3(b.aX, j, X);
-      double vp[6], vhp[6];
+      const bool reload = (par - 1 != prev);
+      if (reload) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { vp[i] = FT(b.aV, (par - 1) * 72 + i); vhp[i] = FT(b.aV, (par - 1) * 72 + 6 + i); }
-      iad_apply(X, vp, V);
-      iad_apply(X, vhp, Vh);
+        for (int i = 0; i < 6; ++i) { V[0][i] = FT(b.aV, (par - 1) * 72 + i); Vh[0][i] = FT(b.aV, (par - 1) * 72 + 6 + i); }
+      }
+      artic_down(X, V[0], Vh[0]);
+      if (ex) {
+#pragma unroll
+        for (int e = 1; e < 1 + NE; ++e) {
+          if (reload) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+              V[e][i] = FT(b.aV, (par - 1) * 72 + e * 12 + i);
+              Vh[e][i] = FT(b.aV, (par - 1) * 72 + e * 12 + 6 + i);
+            }
+          }
+          artic_down(X, V[e], Vh[e]);
+        }
+      }
     }
     const bool useu = !MARKED_U || m.jmark[j];
     for (int c = 0; c < nd; ++c) {
       const int k = dof + c;
+      double LA[6], LM[6], s[6], sh[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        LA[i] = FT(b.aLA, k * 6 + i); LM[i] = FT(b.aLM, k * 6 + i);
+        s[i] = FT(b.aS, k * 6 + i); sh[i] = FT(b.aSh, k * 6 + i);
+      }
       double t = useu ? FT(u, k) : 0.;
       if (par != 0 || c > 0) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) t -= FT(b.aLA, k * 6 + i) * V[i] + FT(b.aLM, k * 6 + i) * Vh[i];
+        for (int i = 0; i < 6; ++i) t -= LA[i] * V[0][i] + LM[i] * Vh[0][i];
       }
       FT(x, k) = t;
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { V[i] += FT(b.aS, k * 6 + i) * t; Vh[i] += FT(b.aSh, k * 6 + i) * t; }
-    }
-    if (m.jhaschild[j] || m.jmark[j]) {
+      for (int i = 0; i < 6; ++i) { V[0][i] += s[i] * t; Vh[0][i] += sh[i] * t; }
+      if (ex) {
+        const int pos = m.dofpos[k];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { FT(b.aV, j * 72 + i) = V[i]; FT(b.aV, j * 72 + 6 + i) = Vh[i]; }
+        for (int e = 0; e < NE; ++e) {
+          const bool onpath = pos < ekc[e] && m.pathdof[eoff[e] + pos] == k;
+          double te = onpath ? FT(b.au, (1 + e) * n + k) : 0.;
+          if (par != 0 || c > 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) te -= LA[i] * V[1 + e][i] + LM[i] * Vh[1 + e][i];
+          }
+          FT(b.ax, e * n + k) = te;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) { V[1 + e][i] += s[i] * te; Vh[1 + e][i] += sh[i] * te; }
+        }
+      }
     }
+    const bool gen = !MARKED_U && m.jmark[j] && artic_is_gen_body(m, j);
+    if (gen || artic_child_reads_aV(m, j, j + 1, false)) {
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { FT(b.aV, j * 72 + i) = V[0][i]; FT(b.aV, j * 72 + 6 + i) = Vh[0][i]; }
+    }
+    if (ex && (gen || artic_child_reads_aV(m, j, j + 1, true))) {
+#pragma unroll
+      for (int e = 1; e < 1 + NE; ++e)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) { FT(b.aV, j * 72 + e * 12 + i) = V[e][i]; FT(b.aV, j * 72 + e * 12 + 6 + i) = Vh[e][i]; }
+    }
+    prev = j;
   }
 }
 
 // ---------------------------------------------------------------------------------------
 // NR right-hand sides that start on ONE root path (unit wrenches on body `body`, or a unit
-// generalized force on dof `kstart`), restricted to the marked joints:
-//  backward along the path (u stored in au[r][k] for the path dofs), then forward over the
-//  marked joints.  (V of each marked body is left in aV[j][r*12 ..], x in ax[r][k].)
+// generalized force on dof `kstart`): leaf-to-root along the path, reduced right-hand sides u
+// to au[ubase + r][k] for the path dofs.
 // `rot` (9 doubles, row-major, or nullptr): the unit wrenches are those of the rotated generator
 // basis G' = blockdiag(R, R) G of a contact-aligned body, i.e. wrench r is row r of blockdiag(R, R).
 template <int NR>
-ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t w, int body, int kstart,
-                                  const double* rot = nullptr) {
+ARB_D void artic_backward_generators(const DevModel& m, const DevBatch& b, int64_t w, int body, int kstart,
+                                     const double* rot = nullptr, int ubase = 0) {
   const int n = m.ndof;
   const int off = m.coloff[body];
   double beta[NR][6];
@@ -499,7 +581,7 @@ ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t 
       for (int i = 0; i < 6; ++i) sb += s[i] * beta[r][i];
       const double tau = (k == kstart) ? 1. : 0.;
       const double u = (tau - sb) * dinv;
-      FT(b.au, r * n + k) = u;
+      FT(b.au, (ubase + r) * n + k) = u;
       if (!last) {
 #pragma unroll
         for (int i = 0; i < 6; ++i) beta[r][i] += U[i] * u;
@@ -517,18 +599,29 @@ ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t 
       }
     }
   }
-  // forward over the marked joints
-  const int kc = l0 + 1;   // path dofs 0..l0 carry a non-zero u
+}
+
+// The NR solutions of artic_backward_generators' right-hand sides (ubase 0) over the marked joints:
+// x to ax[r][k]; V of the generator bodies (and (V, V^) of the bodies a later joint reads) to
+// aV[j][r*12 ..].  CARRY = false: every body's (V, V^) goes through aV (less register pressure).
+template <int NR, bool CARRY>
+ARB_D void artic_forward_generators(const DevModel& m, const DevBatch& b, int64_t w, int body, int kstart) {
+  const int n = m.ndof;
+  const int off = m.coloff[body];
+  const int kc = ((kstart < 0) ? m.kcols[body] - 1 : m.dofpos[kstart]) + 1;   // path dofs 0..kc-1 carry a non-zero u
+  double V[NR][6], Vh[NR][6];
+  int prev = -2;
   for (int j = 0; j < m.nj; ++j) {
     if (!m.jmark[j]) continue;
-    if (j + 1 < m.nj && m.jmark[j + 1]) {
-      arb_prefetch_rows<12>(b.aX + (j + 1) * (12 * ARB_TILE));
-      artic_prefetch_dofs(m, j + 1, b.aLA, b.aLM, b.aS, b.aSh);
+    int jn = j + 1;                       // the next joint of this pass
+    while (jn < m.nj && !m.jmark[jn]) ++jn;
+    if (jn < m.nj) {
+      arb_prefetch_rows<12>(b.aX + jn * (12 * ARB_TILE));
+      artic_prefetch_dofs(m, jn, b.aLA, b.aLM, b.aS, b.aSh);
     }
     const int par = m.jparent[j];
     const int nd = arb_joint_ndof(m.jtype[j]);
     const int dof = m.jdof[j];
-    double V[NR][6], Vh[NR][6];
     if (par == 0) {
 #pragma unroll
       for (int r = 0; r < NR; ++r)
@@ -537,16 +630,17 @@ ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t 
     } else {
       Se3 X;
       load_se3(b.aX, j, X);
+      const bool reload = !CARRY || (par - 1 != prev);
 #pragma unroll
       for (int r = 0; r < NR; ++r) {
-        double vp[6], vhp[6];
+        if (reload) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) {
-          vp[i] = FT(b.aV, (par - 1) * 72 + r * 12 + i);
-          vhp[i] = FT(b.aV, (par - 1) * 72 + r * 12 + 6 + i);
+          for (int i = 0; i < 6; ++i) {
+            V[r][i] = FT(b.aV, (par - 1) * 72 + r * 12 + i);
+            Vh[r][i] = FT(b.aV, (par - 1) * 72 + r * 12 + 6 + i);
+          }
         }
-        iad_apply(X, vp, V[r]);
-        iad_apply(X, vhp, Vh[r]);
+        artic_down(X, V[r], Vh[r]);
       }
     }
     for (int c = 0; c < nd; ++c) {
@@ -571,14 +665,35 @@ ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t 
         for (int i = 0; i < 6; ++i) { V[r][i] += s[i] * t; Vh[r][i] += sh[i] * t; }
       }
     }
+    if (!CARRY || artic_child_reads_aV(m, j, jn, true)) {
 #pragma unroll
-    for (int r = 0; r < NR; ++r)
+      for (int r = 0; r < NR; ++r)
 #pragma unroll
-      for (int i = 0; i < 6; ++i) {
-        FT(b.aV, j * 72 + r * 12 + i) = V[r][i];
-        FT(b.aV, j * 72 + r * 12 + 6 + i) = Vh[r][i];
-      }
+        for (int i = 0; i < 6; ++i) {
+          FT(b.aV, j * 72 + r * 12 + i) = V[r][i];
+          FT(b.aV, j * 72 + r * 12 + 6 + i) = Vh[r][i];
+        }
+    } else if (artic_is_gen_body(m, j)) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) FT(b.aV, j * 72 + r * 12 + i) = V[r][i];
+    }
+    prev = j;
   }
+}
+
+// Carrying (V, V^) of SIX right-hand sides along chains keeps 144 registers live across the joint
+// loop: measured slower (spills, prepare 4.80 vs 4.65 ms per 262144 worlds), so the six-column
+// solves go through aV; the one- to three-column pass above carries.
+#ifndef ARTIC_GEN_CARRY
+#define ARTIC_GEN_CARRY 0
+#endif
+template <int NR>
+ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t w, int body, int kstart,
+                                  const double* rot = nullptr) {
+  artic_backward_generators<NR>(m, b, w, body, kstart, rot, 0);
+  artic_forward_generators<NR, (ARTIC_GEN_CARRY != 0)>(m, b, w, body, kstart);
 }
 
 // row `g` of the generator matrix G applied to the solution r of the last solve:

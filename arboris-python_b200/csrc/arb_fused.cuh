@@ -109,10 +109,10 @@ ARB_D bool constraint_update(const DevModel& m, int c, const Se3& P0, const Se3&
 }
 
 // G applied to the NR solutions of the last articulated solve (x = solutions of the joint-limit
-// rows, V of the generator bodies in aV): out[g * stride + col0 + r] for every generator row g.
+// rows, V of the generator bodies in aV[..][rv0 + r]): out[g * stride + col0 + r] for every generator row g.
 template <int NR>
 ARB_D void fused_gen_rows(const DevModel& m, const DevBatch& b, int64_t w, const double* x, double* out,
-                          int stride, int col0) {
+                          int stride, int col0, int rv0 = 0) {
   for (int gj = 0; gj < m.ngen; ++gj) {
     double Re[9];
     const bool al = m.gen_aligned[gj] != 0;
@@ -123,7 +123,7 @@ ARB_D void fused_gen_rows(const DevModel& m, const DevBatch& b, int64_t w, const
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
       double v[6];
-      artic_gen_block(m, b, gj, r, al ? Re : nullptr, v);
+      artic_gen_block(m, b, gj, rv0 + r, al ? Re : nullptr, v);
 #pragma unroll
       for (int i = 0; i < 6; ++i) FT(out, (6 * gj + i) * stride + col0 + r) = v[i];
     }
@@ -139,7 +139,6 @@ ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, 
   const int NG = m.ngrows;
   artic_kinematics(m, b, w);
   if (!artic_factor(m, b, w, dt)) b.status[w] |= ARB_STATUS_SINGULAR;
-  artic_forward_full<false>(m, b, w, b.au, b.fq);   // q_free
   // frames of the contact-aligned generator bodies: R_e = R_c^T R_body
   for (int gi = 0; gi < m.ngen; ++gi) {
     if (!m.gen_aligned[gi]) continue;
@@ -205,10 +204,26 @@ ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, 
     FT(b.factive, c) = act ? 1 : 0;
     any = any || act;
   }
+  // q_free; the first two joint-limit generators (unit generalized forces) ride along in the same
+  // root-to-leaf pass
+  const int nlim = NG - 6 * m.ngen;
+  const int nm = nlim >= 2 ? 2 : 0;
+  if (nm == 2) {
+    const int ek[2] = {m.glimdof[0], m.glimdof[1]};
+    if (any) {
+      artic_backward_generators<1>(m, b, w, m.dofbody[ek[0]], ek[0], nullptr, 1);
+      artic_backward_generators<1>(m, b, w, m.dofbody[ek[1]], ek[1], nullptr, 2);
+    }
+    artic_forward_full<false, 2>(m, b, w, b.au, b.fq, any, ek);
+  } else {
+    artic_forward_full<false, 0>(m, b, w, b.au, b.fq);
+  }
   if (!any) return;
   // generator space: v0 = G q_free, Lambda = G Z^-1 G^T (column block by column block)
   // (rows of a contact-aligned body are taken in its frame R_e: G' = blockdiag(R_e, R_e) G)
   fused_gen_rows<1>(m, b, w, b.fq, b.fv0, 1, 0);
+  for (int e = 0; e < nm; ++e)
+    fused_gen_rows<1>(m, b, w, b.ax + e * m.ndof * ARB_TILE, b.fLam, NG, 6 * m.ngen + e, 1 + e);
   for (int gi = 0; gi < m.ngen; ++gi) {
     if (m.gen_aligned[gi]) {
       double Re[9];
@@ -220,7 +235,7 @@ ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, 
     }
     fused_gen_rows<6>(m, b, w, b.ax, b.fLam, NG, 6 * gi);
   }
-  for (int h = 6 * m.ngen; h < NG; ++h) {
+  for (int h = 6 * m.ngen + nm; h < NG; ++h) {
     const int k = m.glimdof[h - 6 * m.ngen];
     artic_solve_generators<1>(m, b, w, m.dofbody[k], k);
     fused_gen_rows<1>(m, b, w, b.ax, b.fLam, NG, h);
@@ -1105,7 +1120,7 @@ ARB_D void world_fused_finish(const DevModel& m, const DevBatch& b, int64_t w, d
   // q'+ = q_free + Z^-1 G^T y
   if (any) {
     artic_backward_wrenches(m, b, w, b.fy);
-    artic_forward_full<true>(m, b, w, b.au, b.ax);
+    artic_forward_full<true, 0>(m, b, w, b.au, b.ax);
   }
   bool finite = true;
   for (int j = 0; j < m.nj; ++j) {
