@@ -828,12 +828,15 @@ ARB_D unsigned long long world_fused_gs(const DevModel& m, const DevBatch& b, in
       if (gneed >= 0) gs_cache_load<true>(m, b, w, k, gneed, nneed);
     }
     if (!act) continue;
+    {   // operands of the next visit, also from a joint-limit visit and across the end of a sweep
+      const int cn = (c + 1 < m.nc) ? c + 1 : 0;
+      if (m.ctype[cn] != ARB_CONS_JOINT_LIMITS) gs_prefetch_visit(m, b, cn);
+    }
     if (type == ARB_CONS_JOINT_LIMITS) {
       gs_visit_limit(m, b, c, dt, k);
     } else if (gneed < 0) {
       gs_visit_two_body(m, b, w, c, dt, &status);
     } else {
-      if (c + 1 < m.nc) gs_prefetch_visit(m, b, c + 1);
       if (type == ARB_CONS_BALL_SOCKET) gs_visit_one_body<3>(m, b, w, c, dt, k, &status);
       else if (gs_visit_one_body<4>(m, b, w, c, dt, k, &status) == 3 && c < 32) slid |= 1u << c;
 #ifdef ARB_HOSTTEST_COUNTERS
