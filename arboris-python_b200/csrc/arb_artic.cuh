@@ -423,6 +423,8 @@ ARB_D bool artic_is_gen_body(const DevModel& m, int j) {
     if (m.gen_body[g] == j + 1) return true;
   return false;
 }
+// doubles per joint in aV
+ARB_D int artic_vstride(const DevModel& m) { return 72 * (m.ngen > 1 ? m.ngen : 1); }
 // (V, V^) of the child: X applied in place
 ARB_D void artic_down(const Se3& X, double* V, double* Vh) {
   double a[6], c[6];
@@ -444,6 +446,7 @@ template <bool MARKED_U, int NE>
 ARB_D void artic_forward_full(const DevModel& m, const DevBatch& b, int64_t w, const double* u, double* x,
                               bool ext = false, const int* ek = nullptr) {
   const int n = m.ndof;
+  const int VS = artic_vstride(m);
   double V[1 + NE][6], Vh[1 + NE][6];
   int eoff[NE > 0 ? NE : 1], ekc[NE > 0 ? NE : 1];
 #pragma unroll
@@ -472,7 +475,7 @@ ARB_D void artic_forward_full(const DevModel& m, const DevBatch& b, int64_t w, c
       const bool reload = (par - 1 != prev);
       if (reload) {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { V[0][i] = FT(b.aV, (par - 1) * 72 + i); Vh[0][i] = FT(b.aV, (par - 1) * 72 + 6 + i); }
+        for (int i = 0; i < 6; ++i) { V[0][i] = FT(b.aV, (par - 1) * VS + i); Vh[0][i] = FT(b.aV, (par - 1) * VS + 6 + i); }
       }
       artic_down(X, V[0], Vh[0]);
       if (ex) {
@@ -481,8 +484,8 @@ ARB_D void artic_forward_full(const DevModel& m, const DevBatch& b, int64_t w, c
           if (reload) {
 #pragma unroll
             for (int i = 0; i < 6; ++i) {
-              V[e][i] = FT(b.aV, (par - 1) * 72 + e * 12 + i);
-              Vh[e][i] = FT(b.aV, (par - 1) * 72 + e * 12 + 6 + i);
+              V[e][i] = FT(b.aV, (par - 1) * VS + e * 12 + i);
+              Vh[e][i] = FT(b.aV, (par - 1) * VS + e * 12 + 6 + i);
             }
           }
           artic_down(X, V[e], Vh[e]);
@@ -525,13 +528,13 @@ ARB_D void artic_forward_full(const DevModel& m, const DevBatch& b, int64_t w, c
     const bool gen = !MARKED_U && m.jmark[j] && artic_is_gen_body(m, j);
     if (gen || artic_child_reads_aV(m, j, j + 1, false)) {
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { FT(b.aV, j * 72 + i) = V[0][i]; FT(b.aV, j * 72 + 6 + i) = Vh[0][i]; }
+      for (int i = 0; i < 6; ++i) { FT(b.aV, j * VS + i) = V[0][i]; FT(b.aV, j * VS + 6 + i) = Vh[0][i]; }
     }
     if (ex && (gen || artic_child_reads_aV(m, j, j + 1, true))) {
 #pragma unroll
       for (int e = 1; e < 1 + NE; ++e)
 #pragma unroll
-        for (int i = 0; i < 6; ++i) { FT(b.aV, j * 72 + e * 12 + i) = V[e][i]; FT(b.aV, j * 72 + e * 12 + 6 + i) = Vh[e][i]; }
+        for (int i = 0; i < 6; ++i) { FT(b.aV, j * VS + e * 12 + i) = V[e][i]; FT(b.aV, j * VS + e * 12 + 6 + i) = Vh[e][i]; }
     }
     prev = j;
   }
@@ -607,6 +610,7 @@ ARB_D void artic_backward_generators(const DevModel& m, const DevBatch& b, int64
 template <int NR, bool CARRY>
 ARB_D void artic_forward_generators(const DevModel& m, const DevBatch& b, int64_t w, int body, int kstart) {
   const int n = m.ndof;
+  const int VS = artic_vstride(m);
   const int off = m.coloff[body];
   const int kc = ((kstart < 0) ? m.kcols[body] - 1 : m.dofpos[kstart]) + 1;   // path dofs 0..kc-1 carry a non-zero u
   double V[NR][6], Vh[NR][6];
@@ -636,8 +640,8 @@ ARB_D void artic_forward_generators(const DevModel& m, const DevBatch& b, int64_
         if (reload) {
 #pragma unroll
           for (int i = 0; i < 6; ++i) {
-            V[r][i] = FT(b.aV, (par - 1) * 72 + r * 12 + i);
-            Vh[r][i] = FT(b.aV, (par - 1) * 72 + r * 12 + 6 + i);
+            V[r][i] = FT(b.aV, (par - 1) * VS + r * 12 + i);
+            Vh[r][i] = FT(b.aV, (par - 1) * VS + r * 12 + 6 + i);
           }
         }
         artic_down(X, V[r], Vh[r]);
@@ -670,16 +674,91 @@ ARB_D void artic_forward_generators(const DevModel& m, const DevBatch& b, int64_
       for (int r = 0; r < NR; ++r)
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-          FT(b.aV, j * 72 + r * 12 + i) = V[r][i];
-          FT(b.aV, j * 72 + r * 12 + 6 + i) = Vh[r][i];
+          FT(b.aV, j * VS + r * 12 + i) = V[r][i];
+          FT(b.aV, j * VS + r * 12 + 6 + i) = Vh[r][i];
         }
     } else if (artic_is_gen_body(m, j)) {
 #pragma unroll
       for (int r = 0; r < NR; ++r)
 #pragma unroll
-        for (int i = 0; i < 6; ++i) FT(b.aV, j * 72 + r * 12 + i) = V[r][i];
+        for (int i = 0; i < 6; ++i) FT(b.aV, j * VS + r * 12 + i) = V[r][i];
     }
     prev = j;
+  }
+}
+
+// The six-column solves of ALL generator bodies (right-hand sides of artic_backward_generators with
+// ubase = 6 gi) in ONE root-to-leaf pass over the marked joints: the rows LA, LM, s, s^ and X of a
+// joint come from DRAM once and are re-read from the L1 for the other bodies, instead of once per
+// body in passes far enough apart to miss the L2.  Body gi uses au / ax rows 6 gi .. 6 gi + 5 and
+// aV[j][12 (6 gi + r) ..]; nothing stays in registers from one body to the next.
+ARB_D void artic_forward_generators_all(const DevModel& m, const DevBatch& b, int64_t w) {
+  const int n = m.ndof;
+  const int VS = artic_vstride(m);
+  for (int j = 0; j < m.nj; ++j) {
+    if (!m.jmark[j]) continue;
+    int jn = j + 1;                       // the next joint of this pass
+    while (jn < m.nj && !m.jmark[jn]) ++jn;
+    if (jn < m.nj) {
+      arb_prefetch_rows<12>(b.aX + jn * (12 * ARB_TILE));
+      artic_prefetch_dofs(m, jn, b.aLA, b.aLM, b.aS, b.aSh);
+    }
+    const int par = m.jparent[j];
+    const int nd = arb_joint_ndof(m.jtype[j]);
+    const int dof = m.jdof[j];
+    for (int gi = 0; gi < m.ngen; ++gi) {
+      const int off = m.coloff[m.gen_body[gi]];
+      const int kc = m.kcols[m.gen_body[gi]];   // path dofs 0..kc-1 carry a non-zero u
+      const int rb = 6 * gi;
+      double V[6][6], Vh[6][6];
+      if (par == 0) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int i = 0; i < 6; ++i) { V[r][i] = 0.; Vh[r][i] = 0.; }
+      } else {
+        Se3 X;
+        load_se3(b.aX, j, X);
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+#pragma unroll
+          for (int i = 0; i < 6; ++i) {
+            V[r][i] = FT(b.aV, (par - 1) * VS + (rb + r) * 12 + i);
+            Vh[r][i] = FT(b.aV, (par - 1) * VS + (rb + r) * 12 + 6 + i);
+          }
+          artic_down(X, V[r], Vh[r]);
+        }
+      }
+      for (int c = 0; c < nd; ++c) {
+        const int k = dof + c;
+        const int pos = m.dofpos[k];
+        const bool onpath = pos < kc && m.pathdof[off + pos] == k;
+        double LA[6], LM[6], s[6], sh[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          LA[i] = FT(b.aLA, k * 6 + i); LM[i] = FT(b.aLM, k * 6 + i);
+          s[i] = FT(b.aS, k * 6 + i); sh[i] = FT(b.aSh, k * 6 + i);
+        }
+#pragma unroll
+        for (int r = 0; r < 6; ++r) {
+          double t = onpath ? FT(b.au, (rb + r) * n + k) : 0.;
+          if (par != 0 || c > 0) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) t -= LA[i] * V[r][i] + LM[i] * Vh[r][i];
+          }
+          FT(b.ax, (rb + r) * n + k) = t;
+#pragma unroll
+          for (int i = 0; i < 6; ++i) { V[r][i] += s[i] * t; Vh[r][i] += sh[i] * t; }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+          FT(b.aV, j * VS + (rb + r) * 12 + i) = V[r][i];
+          FT(b.aV, j * VS + (rb + r) * 12 + 6 + i) = Vh[r][i];
+        }
+    }
   }
 }
 
@@ -699,7 +778,7 @@ ARB_D void artic_solve_generators(const DevModel& m, const DevBatch& b, int64_t 
 // row `g` of the generator matrix G applied to the solution r of the last solve:
 // body generators read V of their body, joint-limit generators the dof itself.
 ARB_D double artic_gen_value(const DevModel& m, const DevBatch& b, int64_t w, int g, int r, const double* x) {
-  if (g < 6 * m.ngen) return FT(b.aV, (m.gen_body[g / 6] - 1) * 72 + r * 12 + g % 6);
+  if (g < 6 * m.ngen) return FT(b.aV, (m.gen_body[g / 6] - 1) * artic_vstride(m) + r * 12 + g % 6);
   return FT(x, r * m.ndof + m.glimdof[g - 6 * m.ngen]);
 }
 // the 6 rows of generator body gi applied to solution r: V of the body, rotated into the
@@ -707,7 +786,7 @@ ARB_D double artic_gen_value(const DevModel& m, const DevBatch& b, int64_t w, in
 ARB_D void artic_gen_block(const DevModel& m, const DevBatch& b, int gi, int r, const double* rot, double* out) {
   double V[6];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) V[i] = FT(b.aV, (m.gen_body[gi] - 1) * 72 + r * 12 + i);
+  for (int i = 0; i < 6; ++i) V[i] = FT(b.aV, (m.gen_body[gi] - 1) * artic_vstride(m) + r * 12 + i);
   if (rot != nullptr) {
     m3_mulv(rot, V, out);
     m3_mulv(rot, V + 3, out + 3);

@@ -224,6 +224,22 @@ ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, 
   fused_gen_rows<1>(m, b, w, b.fq, b.fv0, 1, 0);
   for (int e = 0; e < nm; ++e)
     fused_gen_rows<1>(m, b, w, b.ax + e * m.ndof * ARB_TILE, b.fLam, NG, 6 * m.ngen + e, 1 + e);
+#ifndef PREP_GEN_SEPARATE
+  // the generator bodies: leaf-to-root per body, then one root-to-leaf pass for all of them
+  for (int gi = 0; gi < m.ngen; ++gi) {
+    if (m.gen_aligned[gi]) {
+      double Re[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) Re[i] = FT(b.fRe, 9 * gi + i);
+      artic_backward_generators<6>(m, b, w, m.gen_body[gi], -1, Re, 6 * gi);
+    } else {
+      artic_backward_generators<6>(m, b, w, m.gen_body[gi], -1, nullptr, 6 * gi);
+    }
+  }
+  artic_forward_generators_all(m, b, w);
+  for (int gi = 0; gi < m.ngen; ++gi)
+    fused_gen_rows<6>(m, b, w, b.ax + 6 * gi * m.ndof * ARB_TILE, b.fLam, NG, 6 * gi, 6 * gi);
+#else
   for (int gi = 0; gi < m.ngen; ++gi) {
     if (m.gen_aligned[gi]) {
       double Re[9];
@@ -235,6 +251,7 @@ ARB_D void world_fused_prepare(const DevModel& m, const DevBatch& b, int64_t w, 
     }
     fused_gen_rows<6>(m, b, w, b.ax, b.fLam, NG, 6 * gi);
   }
+#endif
   for (int h = 6 * m.ngen + nm; h < NG; ++h) {
     const int k = m.glimdof[h - 6 * m.ngen];
     artic_solve_generators<1>(m, b, w, m.dofbody[k], k);

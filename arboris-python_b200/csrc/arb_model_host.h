@@ -287,7 +287,9 @@ static inline FusedSizes fused_sizes(const HostModel& m) {
   s.factive = nc; s.fbranch = nc; s.fzidx = 3 * nc;
   s.aX = nj * 12; s.atw = nj * 6; s.ath = nj * 6;
   s.aS = s.aSh = s.aU = s.aLA = s.aLM = nn * 6; s.adinv = nn;
-  s.aIA = s.aIM = nj * 36; s.abeta = nj * 6; s.au = 6 * nn; s.ax = 6 * nn; s.aV = nj * 72;
+  s.aIA = s.aIM = nj * 36; s.abeta = nj * 6;
+  const int64_t ng1 = m.ngen > 1 ? m.ngen : 1;   // six right-hand sides per generator body, all bodies in one pass
+  s.au = 6 * ng1 * nn; s.ax = 6 * ng1 * nn; s.aV = nj * 72 * ng1;
   return s;
 }
 // Tiled layout: tile t of ARB_TILE worlds owns doubles [t*R*ARB_TILE, (t+1)*R*ARB_TILE), array X

@@ -124,7 +124,7 @@ struct DevBatch {
   double *adinv;     // [n]        1 / d_k,  d_k = s_k^T U_k (+ PD diagonal)
   double *aIA, *aIM; // [nj][36]   children's contributions to the articulated matrices of body j+1
   double *abeta;     // [nj][6]    children's contributions to the bias wrench
-  double *au;        // [6][n]     reduced right-hand sides u_k, up to 6 at once
-  double *ax;        // [6][n]     solutions
-  double *aV;        // [nj][72]   (V, V^) of each body for up to 6 right-hand sides
+  double *au;        // [6 ngen][n]     reduced right-hand sides u_k, 6 per generator body
+  double *ax;        // [6 ngen][n]     solutions
+  double *aV;        // [nj][72 ngen]   (V, V^) of each body for 6 right-hand sides per generator body
 };
