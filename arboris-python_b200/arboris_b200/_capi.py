@@ -93,6 +93,7 @@ SYMBOLS = [
     ("arb_step_host", _i32, [_vp, _vp, _vp, _vp, c_dblp, _i32]),
     ("arb_step_host_strided", _i32, [_vp, _vp, _vp, _vp, _i64, c_dblp, _i32, _i32]),
     ("arb_batch_synchronize", _i32, [_vp]),
+    ("arb_state_copy_host_strided", _i32, [_vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     ("arb_get_matrix", _i32, [_vp, _i32, _vp, _i64, _i64]),
     ("arb_get_vector", _i32, [_vp, _i32, _vp, _i64, _i64]),
     ("arb_get_body", _i32, [_vp, _i32, _i32, _vp, _i64, _i64]),

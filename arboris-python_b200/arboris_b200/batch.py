@@ -330,8 +330,16 @@ class HostPipeline(object):
     ``gpos``, ``gvel``, ``cforce`` are C-contiguous (elem, W) numpy arrays over PINNED memory
     (e.g. ``torch.empty(...).pin_memory().numpy()``), updated in place."""
 
-    def __init__(self, world_or_model, nworlds, chunks=8, device=None):
+    def __init__(self, world_or_model, nworlds, chunks=8, device=None, mode="streams", compute_streams=1):
+        """``mode="streams"``: one stream per block (copies and kernels of a block in order on it).
+        ``mode="serial"``: the kernels of ALL blocks on one stream, block after block, the copies on
+        two more streams ordered by events -- one kernel on the GPU at a time (kernels of different
+        stages sharing an SM lose a fifth of their throughput once the worlds are sorted), at the
+        price of one partial wave of CTAs per block and stage (``compute_streams`` = 2 lets the next
+        block's kernels fill the tail of the current one's)."""
         from .shard import shard_range
+        assert mode in ("streams", "serial")
+        self.mode = mode
         self.nworlds = int(nworlds)
         if isinstance(chunks, (list, tuple)):
             # relative sizes of the blocks, e.g. (1, 3, 4, 4, 3, 1): small first and last blocks
@@ -348,18 +356,51 @@ class HostPipeline(object):
             self.ranges = [shard_range(self.nworlds, k, chunks) for k in range(chunks)]
         self.ranges = [r for r in self.ranges if r[1] > r[0]]
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        serial = mode == "serial"
+        self._css = [torch.cuda.Stream(dev) for _ in range(max(1, int(compute_streams)))] if serial else None
+        self._hs = torch.cuda.Stream(dev) if serial else None            # host -> device copies
+        self._ds = torch.cuda.Stream(dev) if serial else None            # device -> host copies
         first = BatchedWorld(world_or_model, self.ranges[0][1] - self.ranges[0][0], device=dev,
-                             stream=torch.cuda.Stream(dev))
+                             stream=self._css[0] if serial else torch.cuda.Stream(dev))
         self.model = first.model
-        self.parts = [first] + [BatchedWorld(self.model, w1 - w0, device=dev, stream=torch.cuda.Stream(dev))
-                                for w0, w1 in self.ranges[1:]]
+        self.parts = [first] + [BatchedWorld(self.model, w1 - w0, device=dev,
+                                             stream=self._css[(i + 1) % len(self._css)] if serial
+                                             else torch.cuda.Stream(dev))
+                                for i, (w0, w1) in enumerate(self.ranges[1:])]
+        self._ev = [(torch.cuda.Event(), torch.cuda.Event()) for _ in self.parts] if serial else None
         torch.cuda.synchronize(dev)      # construction ran on the default stream
 
     def set_option(self, name, value):
         for p in self.parts:
             p.set_option(name, value)
 
+    def _copy(self, p, gpos, gvel, cforce, w0, w1, to_device, stream):
+        ld = gpos.strides[0]//8
+        assert gpos.strides[1] == 8 and gvel.strides[1] == 8 and gvel.strides[0]//8 == ld
+        g, v = gpos[:, w0:w1], gvel[:, w0:w1]
+        cf = None
+        if cforce is not None and cforce.size:
+            assert cforce.strides[0]//8 == ld
+            cf = cforce[:, w0:w1].ctypes.data
+        _capi.check(p._lib, p._lib.arb_state_copy_host_strided(
+            p._batch_h, g.ctypes.data, v.ctypes.data, cf, ld, 1 if to_device else 0,
+            C.c_void_p(stream.cuda_stream)))
+
+    def _step_serial(self, gpos, gvel, cforce, dt, nsteps):
+        for (w0, w1), p, (eh, ec) in zip(self.ranges, self.parts, self._ev):
+            self._copy(p, gpos, gvel, cforce, w0, w1, True, self._hs)
+            eh.record(self._hs)
+        for (w0, w1), p, (eh, ec) in zip(self.ranges, self.parts, self._ev):
+            p._stream.wait_event(eh)
+            p.step(dt, nsteps)
+            ec.record(p._stream)
+            self._ds.wait_event(ec)
+            self._copy(p, gpos, gvel, cforce, w0, w1, False, self._ds)
+        self._ds.synchronize()
+
     def step(self, gpos, gvel, cforce, dt, nsteps=1):
+        if self.mode == "serial":
+            return self._step_serial(gpos, gvel, cforce, dt, nsteps)
         for (w0, w1), p in zip(self.ranges, self.parts):
             p.step_host_async(gpos[:, w0:w1], gvel[:, w0:w1],
                               cforce[:, w0:w1] if cforce is not None and cforce.size else None, dt, nsteps)

@@ -358,6 +358,25 @@ extern "C" int arb_step_host_strided(arb_batch* b, double* h_gpos, double* h_gve
   if (synchronize) CUDA_OK(cudaStreamSynchronize(b->stream));
   return 0;
 }
+extern "C" int arb_state_copy_host_strided(arb_batch* b, double* h_gpos, double* h_gvel, double* h_cforce,
+                                           int64_t host_ld, int to_device, void* stream) {
+  int rc = check_bound(b); if (rc) return rc;
+  if (!h_gpos || !h_gvel) { arb_set_error("null host state pointer"); return -1; }
+  if (host_ld < b->d.W) { arb_set_error("host_ld smaller than the number of worlds"); return -1; }
+  CUDA_OK(cudaSetDevice(b->device));
+  const HostModel& h = b->model->host;
+  const size_t W = (size_t)b->d.W, dp = sizeof(double) * W, hp = sizeof(double) * (size_t)host_ld;
+  double* dev[3] = {b->d.gpos, b->d.gvel, b->d.cforce};
+  double* host[3] = {h_gpos, h_gvel, h_cforce};
+  const int rows[3] = {h.ngpos, h.ndof, h_cforce ? h.nrows : 0};
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int a = 0; a < 3; ++a) {
+    if (rows[a] <= 0) continue;
+    if (to_device) CUDA_OK(cudaMemcpy2DAsync(dev[a], dp, host[a], hp, dp, rows[a], cudaMemcpyHostToDevice, st));
+    else CUDA_OK(cudaMemcpy2DAsync(host[a], hp, dev[a], dp, dp, rows[a], cudaMemcpyDeviceToHost, st));
+  }
+  return 0;
+}
 extern "C" int arb_batch_synchronize(arb_batch* b) {
   if (!b) { arb_set_error("null argument"); return -1; }
   CUDA_OK(cudaSetDevice(b->device));

@@ -60,9 +60,13 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.)
-    ap.add_argument("--e2e-chunks", type=lambda t: [int(x) for x in t.split(",")] if "," in t else int(t), default=8,
-                    help="column blocks (each on its own stream) of the end-to-end pass; 1 = one "
-                         "synchronous arb_step_host call per step")
+    ap.add_argument("--e2e-chunks", type=lambda t: [int(x) for x in t.split(",")] if "," in t else int(t), default=[1, 2, 2, 2, 1],
+                    help="column blocks of the end-to-end pass: a number of equal blocks or their relative "
+                         "sizes (a,b,c,...); 1 = one synchronous arb_step_host call per step")
+    ap.add_argument("--e2e-mode", default="serial", choices=["serial", "streams"],
+                    help="HostPipeline mode: 'serial' = the kernels of all blocks on --e2e-compute-streams "
+                         "streams, block after block, copies on two more streams; 'streams' = one stream per block")
+    ap.add_argument("--e2e-compute-streams", type=int, default=3)
     ap.add_argument("--opt", action="append", help="arb_batch_set_option switch, name=value (A/B runs)")
     return ap.parse_args()
 
@@ -277,7 +281,8 @@ def run_ours(a):
         if isinstance(a.e2e_chunks, list) or a.e2e_chunks > 1:
             # the public end-to-end call: column blocks of the host state, one stream each, so
             # that copies and kernels of different blocks overlap (batch.HostPipeline)
-            pipe = HostPipeline(model, W, chunks=a.e2e_chunks, device=bw.device)
+            pipe = HostPipeline(model, W, chunks=a.e2e_chunks, device=bw.device, mode=a.e2e_mode,
+                                compute_streams=a.e2e_compute_streams)
             for opt in (a.opt or []):
                 name, val = opt.split("=")
                 pipe.set_option(name, int(val))
@@ -371,10 +376,15 @@ def run_ours(a):
         out["e2e"] = {"value": total_worlds/(e2e_ms*1e-3), "unit": "world-steps/s",
                       "h2d_bytes_per_step": e2e[1]*world_size, "d2h_bytes_per_step": e2e[2]*world_size,
                       "steps": e2e[3], "chunks": a.e2e_chunks,
-                      "how": ("HostPipeline.step (arb_step_host_strided on %d column blocks, one stream "
-                              "each): pinned host state -> device, 1 step, device -> host, all blocks "
-                              "synchronised, every step; same staggered episodes as the timed region"
-                              % (len(a.e2e_chunks) if isinstance(a.e2e_chunks, list) else a.e2e_chunks))
+                      "mode": a.e2e_mode,
+                      "how": ("HostPipeline.step (%d column blocks of the pinned host state; %s): host -> "
+                              "device, 1 step, device -> host, all blocks synchronised, every step; same "
+                              "staggered episodes as the timed region"
+                              % (len(a.e2e_chunks) if isinstance(a.e2e_chunks, list) else a.e2e_chunks,
+                                 ("kernels of all blocks on %d streams, block after block, "
+                                  "arb_state_copy_host_strided copies on two more streams ordered by events"
+                                  % a.e2e_compute_streams) if a.e2e_mode == "serial"
+                                 else "arb_step_host_strided, one stream per block"))
                              if (isinstance(a.e2e_chunks, list) or a.e2e_chunks > 1) else
                              "arb_step_host: pinned host state -> device, 1 step, device -> host, "
                              "synchronised, every step; same staggered episodes as the timed region"}

@@ -181,6 +181,13 @@ int arb_step_host_strided(arb_batch *batch, double *h_gpos, double *h_gvel, doub
                           int64_t host_ld, const double *dts, int nsteps, int synchronize);
 /* wait for everything enqueued on the batch's stream */
 int arb_batch_synchronize(arb_batch *batch);
+/* the two copies of arb_step_host_strided alone, on a stream of the caller's choice (cudaStream_t):
+ * to_device != 0: host slice -> the batch's bound state arrays; 0: the reverse.  Lets a caller keep
+ * the kernels of all column blocks on ONE stream (one kernel on the GPU at a time) and the copies on
+ * two others, ordered by events (batch.HostPipeline, mode "serial").  Same state arrays as
+ * World._gvel / Joint.gpos in the reference (core.py:626-629). */
+int arb_state_copy_host_strided(arb_batch *batch, double *h_gpos, double *h_gvel, double *h_cforce,
+                                int64_t host_ld, int to_device, void *stream);
 
 /* read-backs into DEVICE buffers, worlds [w0, w1), world-major: out[w-w0][...] */
 int arb_get_matrix(arb_batch *batch, int which, double *out, int64_t w0, int64_t w1);

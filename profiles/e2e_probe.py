@@ -34,18 +34,20 @@ def timeit(fn, steps=30):
 
 import os
 SORT = int(os.environ.get("PROBE_SORT_PERIOD", "-1"))
+MODE = os.environ.get("PROBE_MODE", "streams")
+NCS = int(os.environ.get("PROBE_COMPUTE_STREAMS", "1"))
 
 
 def run(chunks):
     hg.copy_(g0); hv.copy_(v0); hf.zero_()
-    pipe = HostPipeline(model, W, chunks=chunks)
+    pipe = HostPipeline(model, W, chunks=chunks, mode=MODE, compute_streams=NCS)
     if SORT >= 0:
         pipe.set_option("sort_period", SORT)
     hgn, hvn, hfn = hg.numpy(), hv.numpy(), hf.numpy()
     for _ in range(120):                      # into contact
         pipe.step(hgn, hvn, hfn, DT, 1)
     full = timeit(lambda: pipe.step(hgn, hvn, hfn, DT, 1))
-    copies = timeit(lambda: pipe.step(hgn, hvn, hfn, DT, 0))
+    copies = timeit(lambda: pipe.step(hgn, hvn, hfn, DT, 0)) if MODE == "streams" else float("nan")
 
     def compute():
         for p in pipe.parts:
@@ -53,7 +55,7 @@ def run(chunks):
         for p in pipe.parts:
             p.synchronize()
     comp = timeit(compute)
-    print('sort_period=%d ' % SORT + 'chunks=%s: full %.2f ms (%.3g w-s/s)  copies only %.2f ms  compute only %.2f ms'
+    print('mode=%s/%d sort_period=%d ' % (MODE, NCS, SORT) + 'chunks=%s: full %.2f ms (%.3g w-s/s)  copies only %.2f ms  compute only %.2f ms'
           % (chunks, full, W/full*1e3, copies, comp), flush=True)
     pipe.close()
 

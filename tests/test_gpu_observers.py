@@ -104,8 +104,10 @@ def test_energy_monitor_matches_mass_matrix():
     assert np.abs(e[-1] - e[0]).max() < 2e-2*np.abs(e[0]).max()      # semi-implicit Euler, dt = 1 ms
 
 
-def test_host_pipeline_equals_device_step():
-    """HostPipeline (column blocks of pinned host state, one stream each, arb_step_host_strided)
+@pytest.mark.parametrize("mode", ["streams", "serial"])
+def test_host_pipeline_equals_device_step(mode):
+    """HostPipeline (column blocks of pinned host state; one stream each with arb_step_host_strided,
+    or all kernels on one stream and the copies of arb_state_copy_host_strided on two others)
     gives bit for bit the states of the device-resident step, for a batch that does not split evenly."""
     import torch
     from arboris_b200 import scenarios
@@ -118,7 +120,7 @@ def test_host_pipeline_equals_device_step():
     hg = torch.as_tensor(gp).pin_memory()
     hv = torch.as_tensor(gv).pin_memory()
     hf = torch.zeros((model.nrows, W), dtype=torch.float64).pin_memory()
-    pipe = HostPipeline(model, W, chunks=7, device="cuda:0")
+    pipe = HostPipeline(model, W, chunks=7, device="cuda:0", mode=mode)
     for _ in range(90):
         pipe.step(hg.numpy(), hv.numpy(), hf.numpy(), 1e-3, 1)
     bw.step(1e-3, 90)
