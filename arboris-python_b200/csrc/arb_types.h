@@ -18,7 +18,9 @@ ARB_HDI int arb_cons_ndol(int t) {
   return t == ARB_CONS_JOINT_LIMITS ? 1 : t == ARB_CONS_BALL_SOCKET ? 3 : 4;
 }
 
+#ifndef ARB_TILE
 #define ARB_TILE 32          /* worlds per tile of the fused scratch ([W/32][elem][32]) */
+#endif
 
 #define ARB_BODY_MASSIVE 1   /* some entry of the mass matrix > 0 (WeightController.init, controllers.py:37) */
 #define ARB_BODY_HASMASS 2   /* mass matrix not identically zero */
