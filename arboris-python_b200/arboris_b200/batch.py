@@ -324,37 +324,27 @@ class BatchedWorld(object):
 
 class HostPipeline(object):
     """End-to-end stepping of HOST state: the worlds are split into ``chunks`` column blocks, each
-    with its own ``BatchedWorld`` on its own CUDA stream, so that the host->device copy of one
-    block, the kernels of another and the device->host copy of a third overlap (PCIe is full
-    duplex; the step of 262144 human36 worlds and the two 268 MB copies take about as long).
+    with its own ``BatchedWorld``, so that the host->device copy of one block, the kernels of
+    another and the device->host copy of a third overlap (PCIe is full duplex; the step of 262144
+    human36 worlds and the two 268 MB copies take about as long).
     ``gpos``, ``gvel``, ``cforce`` are C-contiguous (elem, W) numpy arrays over PINNED memory
     (e.g. ``torch.empty(...).pin_memory().numpy()``), updated in place."""
 
-    def __init__(self, world_or_model, nworlds, chunks=8, device=None, mode="streams", compute_streams=1):
-        """``mode="streams"``: one stream per block (copies and kernels of a block in order on it).
-        ``mode="serial"``: the kernels of ALL blocks on one stream, block after block, the copies on
-        two more streams ordered by events -- one kernel on the GPU at a time (kernels of different
-        stages sharing an SM lose a fifth of their throughput once the worlds are sorted), at the
-        price of one partial wave of CTAs per block and stage (``compute_streams`` = 2 lets the next
-        block's kernels fill the tail of the current one's)."""
-        from .shard import shard_range
+    def __init__(self, world_or_model, nworlds, chunks=(1, 2, 2, 2, 1), device=None, mode="serial",
+                 compute_streams=3):
+        """``chunks``: number of equal column blocks or their relative sizes (``shard.block_ranges``).
+        ``mode="serial"`` (default): the kernels of ALL blocks on ``compute_streams`` streams, block
+        after block, the copies on two more streams ordered by events -- few kernels on the GPU at a
+        time (kernels of different stages sharing an SM lose a fifth of their throughput once the
+        worlds are sorted); with one compute stream every block and stage ends in a partial wave of
+        CTAs that nothing fills, two or three streams measured best (profiles/README.md).
+        ``mode="streams"``: one stream per block (copies and kernels of a block in order on it,
+        ``arb_step_host_strided``)."""
+        from .shard import block_ranges
         assert mode in ("streams", "serial")
         self.mode = mode
         self.nworlds = int(nworlds)
-        if isinstance(chunks, (list, tuple)):
-            # relative sizes of the blocks, e.g. (1, 3, 4, 4, 3, 1): small first and last blocks
-            # shorten the exposed first copy-in / last copy-out, large middle blocks keep the
-            # kernels efficient
-            tot = float(sum(chunks))
-            edges = [0]
-            for c in chunks:
-                edges.append(min(self.nworlds, max(edges[-1], int(round(self.nworlds*sum(chunks[:len(edges)])/tot/32.))*32)))
-            edges[-1] = self.nworlds
-            self.ranges = list(zip(edges[:-1], edges[1:]))
-        else:
-            chunks = max(1, min(int(chunks), (self.nworlds + 31)//32))
-            self.ranges = [shard_range(self.nworlds, k, chunks) for k in range(chunks)]
-        self.ranges = [r for r in self.ranges if r[1] > r[0]]
+        self.ranges = block_ranges(self.nworlds, chunks)
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         serial = mode == "serial"
         self._css = [torch.cuda.Stream(dev) for _ in range(max(1, int(compute_streams)))] if serial else None

@@ -27,6 +27,31 @@ def shard_range(total, rank, world_size):
     return w0, w0 + q + (1 if rank < r else 0)
 
 
+def block_ranges(total, chunks, align=32):
+    """Column blocks [w0, w1) of a host-resident batch (``batch.HostPipeline``): ``chunks`` is a
+    number of equal blocks, or the relative sizes of the blocks (e.g. ``(1, 2, 2, 2, 1)``: small
+    first and last blocks shorten the exposed first copy-in / last copy-out, large middle blocks
+    keep the kernels efficient).  Relative blocks start on multiples of ``align`` worlds (a tile of
+    the scratch); empty blocks are dropped; the blocks cover [0, total) exactly, in order."""
+    total = int(total)
+    if total < 0:
+        raise ValueError("negative number of worlds")
+    if isinstance(chunks, (list, tuple)):
+        if not chunks or any(c < 0 for c in chunks) or sum(chunks) <= 0:
+            raise ValueError("relative block sizes must be non-negative with a positive sum")
+        tot = float(sum(chunks))
+        edges = [0]
+        for k in range(len(chunks)):
+            e = int(round(total*sum(chunks[:k + 1])/tot/float(align)))*align
+            edges.append(min(total, max(edges[-1], e)))
+        edges[-1] = total
+        ranges = list(zip(edges[:-1], edges[1:]))
+    else:
+        n = max(1, min(int(chunks), (total + align - 1)//align))
+        ranges = [shard_range(total, k, n) for k in range(n)]
+    return [r for r in ranges if r[1] > r[0]]
+
+
 def reduce_report(maxes, sums, device=None, group=None):
     """All-reduce a report: ``maxes`` (e.g. timed milliseconds) with MAX over
     ranks, ``sums`` (world counts, launch counts, non-finite counts) with SUM.

@@ -67,3 +67,29 @@ def test_two_rank_gloo_shards_cover_the_batch(tmp_path):
     assert rep["sums"][0] == total
     np.testing.assert_allclose(rep["sums"][1], gp.sum(), rtol=1e-12)
     np.testing.assert_allclose(rep["sums"][2], gv.sum(), rtol=1e-12, atol=1e-12)
+
+
+def test_block_ranges_cover_the_batch_in_order():
+    """HostPipeline's column blocks: equal or relative sizes, aligned, exact cover, no empty block."""
+    from arboris_b200.shard import block_ranges
+    for total in (0, 1, 31, 32, 1000, 4096, 262144):
+        for chunks in (1, 3, 7, 8, 64, (1, 2, 1), (1, 2, 2, 2, 1), [1, 3, 4, 4, 3, 1], (0, 1, 0)):
+            r = block_ranges(total, chunks)
+            assert all(w1 > w0 for w0, w1 in r)
+            if total == 0:
+                assert r == []
+                continue
+            assert r[0][0] == 0 and r[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(r[:-1], r[1:]))
+            if isinstance(chunks, (list, tuple)):
+                assert all(w0 % 32 == 0 for w0, _ in r)
+    assert block_ranges(262144, (1, 2, 2, 2, 1)) == [(0, 32768), (32768, 98304), (98304, 163840),
+                                                     (163840, 229376), (229376, 262144)]
+    assert block_ranges(1000, 7) == [(0, 143), (143, 286), (286, 429), (429, 572), (572, 715), (715, 858), (858, 1000)]
+    import pytest
+    with pytest.raises(ValueError):
+        block_ranges(10, ())
+    with pytest.raises(ValueError):
+        block_ranges(10, (1, -1))
+    with pytest.raises(ValueError):
+        block_ranges(-1, 2)
