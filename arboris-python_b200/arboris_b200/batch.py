@@ -330,7 +330,7 @@ class HostPipeline(object):
     ``gpos``, ``gvel``, ``cforce`` are C-contiguous (elem, W) numpy arrays over PINNED memory
     (e.g. ``torch.empty(...).pin_memory().numpy()``), updated in place."""
 
-    def __init__(self, world_or_model, nworlds, chunks=(1, 2, 2, 2, 1), device=None, mode="serial",
+    def __init__(self, world_or_model, nworlds, chunks=(1, 1, 2, 2, 2, 1, 1), device=None, mode="serial",
                  compute_streams=3):
         """``chunks``: number of equal column blocks or their relative sizes (``shard.block_ranges``).
         ``mode="serial"`` (default): the kernels of ALL blocks on ``compute_streams`` streams, block

@@ -60,7 +60,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.)
-    ap.add_argument("--e2e-chunks", type=lambda t: [int(x) for x in t.split(",")] if "," in t else int(t), default=[1, 2, 2, 2, 1],
+    ap.add_argument("--e2e-chunks", type=lambda t: [int(x) for x in t.split(",")] if "," in t else int(t), default=[1, 1, 2, 2, 2, 1, 1],
                     help="column blocks of the end-to-end pass: a number of equal blocks or their relative "
                          "sizes (a,b,c,...); 1 = one synchronous arb_step_host call per step")
     ap.add_argument("--e2e-mode", default="serial", choices=["serial", "streams"],
