@@ -239,10 +239,17 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
     d.cforce = d.gvel + (int64_t)h.ndof * W;
     d.status = f->pstatus;
   };
-  if (f->sorted) {
+  // (a call whose first step re-sorts anyway does not gather first: the caller's arrays are the
+  // state at that point -- one gather and one scatter less per sort for callers that step once per
+  // call, like the end-to-end pipeline)
+  const bool sort_first = nsteps > 0 && f->perm[0] != nullptr && b->sort_period > 0 && f->steps > 0 &&
+                          (f->steps % b->sort_period) == 0;
+  bool priv_valid = false;
+  if (f->sorted && !sort_first) {
     rc = fused_state_sync(b, true);
     if (rc) return rc;
     point_at_private();
+    priv_valid = true;
   }
   for (int s = 0; s < nsteps; ++s) {
     const double dt = dts[s];
@@ -252,7 +259,7 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
       // worlds with the most contact work are dispatched first and the grid's tail is made of the
       // cheap ones (stable: ties keep their order).  Done BEFORE the step, so that after a step the scratch read-backs
       // (arb_get_constraint) still see the assignment the step ran with.
-      if (f->sorted) fused_state_sync(b, false);
+      if (f->sorted && priv_valid) fused_state_sync(b, false);
       const int nb = b->m.nc < 32 ? b->m.nc : 32;
       const int c = f->cur;
       CUDA_OKF(cub::DeviceRadixSort::SortPairsDescending(f->cub_tmp, f->cub_bytes, f->key[c], f->key[c ^ 1], f->perm[c],
@@ -265,6 +272,7 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
       b->launches += 1;
       fused_state_sync(b, true);
       point_at_private();
+      priv_valid = true;
     }
     if (ev[0]) cudaEventRecord(ev[0], b->stream);
     k_fused_prepare_lane<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, d, dt);

@@ -294,8 +294,8 @@ def run_ours(a):
                 else:
                     bw.step_host(hgn, hvn, hfn, DT, 1)    # H2D state, 1 step, D2H state, sync
         hep.step_fn = host_steps
-        k_e2e = max(3, min(a.steps, 50))
-        hep.advance(3)
+        k_e2e = max(3, min(a.steps, 100))
+        hep.advance(max(3, min(a.warmup, 8)))    # the blocks' first sorts happen here
         barrier()
         t0 = time.perf_counter()
         hep.advance(k_e2e)
