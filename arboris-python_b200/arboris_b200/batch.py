@@ -63,6 +63,14 @@ class BatchedWorld(object):
                        np.repeat(np.asarray(m.cforce0)[:, None], W, 1) if m.nrows else None)
         self._current_time = 0.
         self._pinned = None
+        self._ctrl_params = {}
+        why = C.c_char_p()
+        if self._lib.arb_batch_step_path(self._batch_h, C.byref(why)) == 0:
+            # not silent: the fused stages fold controllers per dof; anything else runs the
+            # (much slower) phase kernels
+            import warnings
+            warnings.warn("arboris_b200: step() runs the four phase kernels for this model, not the "
+                          "fused stages (%s)" % (why.value or b"").decode(), RuntimeWarning, stacklevel=2)
 
     # ---- plumbing -----------------------------------------------------------------
     def _bind(self):
@@ -113,6 +121,36 @@ class BatchedWorld(object):
     def get_state(self):
         return self.gpos.cpu().numpy(), self.gvel.cpu().numpy(), \
             self.cforce[:int(self.model.nrows)].cpu().numpy()
+
+    # ---- per-world controller parameters -------------------------------------------------------
+    def pd_dofs(self):
+        """dof of each row of the per-world PD parameter arrays (controllers in registration
+        order, each controller's dofs in its own order)."""
+        n = self._lib.arb_model_pd_dofs(self._model_h, None, 0)
+        out = (C.c_int32*max(n, 1))()
+        self._lib.arb_model_pd_dofs(self._model_h, out, n)
+        return [int(out[i]) for i in range(n)]
+
+    def set_controller_params(self, kp=None, kd=None, gpos_des=None, gvel_des=None):
+        """Per-world ``kp``, ``kd`` (diagonal gains), ``gpos_des``, ``gvel_des`` of the
+        ProportionalDerivativeControllers (reference controllers.py:63-159, one value per
+        controller object there): arrays (npd, W), rows as ``pd_dofs()``.  ``None`` keeps what was
+        bound before for that parameter; ``False`` goes back to the model's value."""
+        npd = len(self.pd_dofs())
+        for name, v in (("kp", kp), ("kd", kd), ("gpos_des", gpos_des), ("gvel_des", gvel_des)):
+            if v is None:
+                continue
+            if v is False:
+                self._ctrl_params.pop(name, None)
+                continue
+            t = torch.as_tensor(np.ascontiguousarray(v) if isinstance(v, np.ndarray) else v,
+                                dtype=torch.float64).to(self.device).contiguous()
+            if tuple(t.shape) != (npd, self.nworlds):
+                raise ValueError("%s must have shape (%d, %d)" % (name, npd, self.nworlds))
+            self._ctrl_params[name] = t
+        ptr = [self._ctrl_params[k].data_ptr() if k in self._ctrl_params else None
+               for k in ("kp", "kd", "gpos_des", "gvel_des")]
+        _capi.check(self._lib, self._lib.arb_batch_bind_controller_params(self._batch_h, *ptr))
 
     # ---- the four phases and the fused step ---------------------------------------------
     def update_dynamic(self):

@@ -499,7 +499,18 @@ class World(NamedObject):
     gforce = property(lambda self: self._gforce.copy())
 
     # ---- the step, on the GPU -----------------------------------------------
-    def _device(self):
+    def _device(self, refresh=False):
+        """The single-world device batch.  The reference reads constraint and controller
+        parameters live at every step (``is_enabled()`` core.py:913, ``gpos_des`` / ``kp``
+        controllers.py:141-159, ``_min`` / ``_max`` constraints.py:73-90, ``_mu``, body masses):
+        with ``refresh`` (the start of a step) the world is flattened again and the device model is
+        rebuilt when any parameter differs from the one the batch was made from, so scripts that
+        retarget a PD set-point or toggle a contact between steps behave as they do there."""
+        if self._batch is not None and refresh:
+            from .flatten import flatten
+            if not self._batch.model.same_parameters(flatten(self)):
+                self._batch.close()
+                self._batch = None
         if self._batch is None:
             from .batch import BatchedWorld
             self._batch = BatchedWorld(self, nworlds=1)
@@ -510,7 +521,7 @@ class World(NamedObject):
 
     def update_dynamic(self):
         """core.py:682-734, executed by ``arb_update_dynamic``."""
-        b = self._device()
+        b = self._device(refresh=True)
         b.push_host_state(self)
         b.update_dynamic()
         b.pull_dynamic(self)

@@ -80,6 +80,21 @@ class FlatModel(object):
     def save(self, path):
         np.savez(path, **self.to_dict())
 
+    # fields that hold state (flatten() copies the world's current gpos / gvel / forces there), not
+    # parameters: a model does not change because the world moved
+    _STATE_FIELDS = ("gpos0", "gvel0", "cforce0")
+
+    def same_parameters(self, other):
+        """True when ``other`` describes the same model: topology, constants, constraint and
+        controller parameters, enable flags (everything but the initial state)."""
+        for k in _FIELDS:
+            if k in self._STATE_FIELDS:
+                continue
+            a, b = np.asarray(getattr(self, k)), np.asarray(getattr(other, k))
+            if a.shape != b.shape or not np.array_equal(a, b):
+                return False
+        return True
+
     @classmethod
     def load(cls, path):
         with np.load(path, allow_pickle=False) as z:

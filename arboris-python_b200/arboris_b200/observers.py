@@ -5,7 +5,10 @@ Mirrors of the reference's ``arboris/observers.py`` for ``BatchedWorld``:
 * ``BatchedHdf5Logger``  <- ``Hdf5Logger`` (observers.py:133-289): ``timeline``, ``gpositions/``,
   ``gvelocities/``, ``transforms/`` with the reference's names and shapes, plus ONE extra axis
   for the worlds right after the step axis (dropped with ``squeeze=True`` when one world is
-  logged, which gives exactly the reference's file).  h5py is not needed: the file is written
+  logged, which gives the reference's ``flat=True`` datasets: ``timeline``, per-joint ``gpositions`` /
+  ``gvelocities``, ``transforms`` of the ground and of every moving body).  NOT written: the
+  transforms of the contacts' ``MovingSubFrame``s (observers.py:238-239; the fused step does not
+  materialise contact frames) and the ``model/`` group (``save_model``, observers.py:245-252).  h5py is not needed: the file is written
   by ``arboris_b200.h5write`` (or as ``.npz`` with the same keys).
 * ``BatchedEnergyMonitor`` <- ``EnergyMonitor`` (observers.py:14-54), one value per world.
 
@@ -115,9 +118,14 @@ class BatchedHdf5Logger(Observer):
             root["gpositions"], root["gvelocities"] = gpos, gvel
         if self._save_transforms:
             P = self._poses[:n].cpu().numpy()
-            names = self._names(list(m.body_names)[1:] if len(m.body_names) == nj + 1
-                                else list(m.body_names), "Body", nj)
+            has_ground = len(m.body_names) == nj + 1
+            names = self._names(list(m.body_names)[1:] if has_ground else list(m.body_names), "Body", nj)
             root["transforms"] = {name: fix(P[:, i]) for i, name in enumerate(names)}
+            # the ground is a body too (World.iterbodies, observers.py:233-235): identity
+            gname = (m.body_names[0] if has_ground and m.body_names[0] else "ground")
+            if gname not in root["transforms"]:
+                eye = np.broadcast_to(np.eye(4), P[:, 0].shape).copy()
+                root["transforms"][gname] = fix(eye)
         for g in [g for g in self._group.split("/") if g][::-1]:
             root = {g: root}
         return root

@@ -250,30 +250,89 @@ def _free_and_linear(model):
     return free, lin
 
 
+def _rotzyx_stack(r):
+    """(W, 4, 4) stack of ``Hg.rotzyx(*r[i])`` (same closed form, evaluated on arrays)."""
+    sz, cz = np.sin(r[:, 0]), np.cos(r[:, 0])
+    sy, cy = np.sin(r[:, 1]), np.cos(r[:, 1])
+    sx, cx = np.sin(r[:, 2]), np.cos(r[:, 2])
+    H = np.zeros((r.shape[0], 4, 4))
+    H[:, 0, 0], H[:, 0, 1], H[:, 0, 2] = cz*cy, cz*sy*sx - sz*cx, cz*sy*cx + sz*sx
+    H[:, 1, 0], H[:, 1, 1], H[:, 1, 2] = sz*cy, sz*sy*sx + cz*cx, sz*sy*cx - cz*sx
+    H[:, 2, 0], H[:, 2, 1], H[:, 2, 2] = -sy, cy*sx, cy*cx
+    H[:, 3, 3] = 1.
+    return H
+
+
+def _matmul44(A, B):
+    """Stacked 4x4 products with a fixed summation order (independent of the stack size, so a
+    world's state does not depend on how many worlds are generated with it)."""
+    out = np.zeros(np.broadcast_shapes(A.shape, B.shape))
+    for k in range(4):
+        out += A[..., :, k:k + 1]*B[..., k:k + 1, :]
+    return out
+
+
+# human36_contact: SURVEY.md section 8(d) config 3 -- root lifted by U(0, 0.05) m (left-multiplied
+# as in tests/test_human36_falling.py:16-18), tilted by U(-.05, .05)^3 rad, joint angles U(-.1, .1),
+# zero velocity.  (Round 1 used lift U(0.02, 0.07), tilt +-0.02.)
+CONTACT_LIFT = (0., 0.05)
+CONTACT_TILT = 0.05
+
+
+def _human36_states(model, scenario, w0, w1):
+    """Vectorised seeded states of the two humanoid scenarios: the per-world random draws
+    (``default_rng(SEED0 + w)``) stay per world, the matrix algebra is batched."""
+    W = w1 - w0
+    free, lin = _free_and_linear(model)
+    nlin = int(lin.sum())
+    gpos = np.repeat(np.array(model.gpos0, dtype=float)[:, None], W, 1)
+    gvel = np.repeat(np.array(model.gvel0, dtype=float)[:, None], W, 1)
+    ang = np.empty((W, nlin))
+    t = np.zeros((W, 3))
+    r = np.empty((W, 3))
+    vel = np.empty((W, model.ndof)) if scenario == "human36_free" else None
+    for i in range(W):
+        rng = np.random.default_rng(SEED0 + w0 + i)
+        if scenario == "human36_free":
+            ang[i] = rng.uniform(-0.5, 0.5, nlin)
+            t[i] = rng.uniform([-.1, 0., -.1], [.1, .2, .1])
+            r[i] = rng.uniform(-.3, .3, 3)
+            vel[i] = rng.uniform(-1., 1., model.ndof)
+        else:
+            ang[i] = rng.uniform(-0.1, 0.1, nlin)
+            t[i, 1] = rng.uniform(*CONTACT_LIFT)
+            r[i] = rng.uniform(-CONTACT_TILT, CONTACT_TILT, 3)
+    gpos[lin] = ang.T
+    g = int(model.joint_gpos[free[0]])
+    H0 = np.array(model.gpos0, dtype=float)[g:g + 16].reshape(4, 4)
+    T = np.zeros((W, 4, 4))
+    T[:, range(4), range(4)] = 1.
+    T[:, 0:3, 3] = t
+    R = _rotzyx_stack(r)
+    if scenario == "human36_free":
+        H = _matmul44(_matmul44(T, R), H0[None])
+        gvel[:] = vel.T
+    else:
+        H = _matmul44(T, _matmul44(H0[None], R))
+    gpos[g:g + 16] = H.reshape(W, 16).T
+    for c in range(len(model.cons_type)):       # limited joints start strictly inside their limits
+        if int(model.cons_type[c]) == 0:
+            k = int(model.cons_int[c][2])
+            mn, mx, prox = model.cons_dbl[c][0:3]
+            gpos[k] = np.minimum(np.maximum(gpos[k], mn + 2*prox), mx - 2*prox)
+    return gpos, gvel
+
+
 def initial_state(model, scenario, w):
     """(gpos, gvel) of world ``w`` for ``scenario``; deterministic in ``w``."""
+    if scenario in ("human36_free", "human36_contact"):
+        gp, gv = _human36_states(model, scenario, int(w), int(w) + 1)
+        return gp[:, 0], gv[:, 0]
     rng = np.random.default_rng(SEED0 + int(w))
     gpos = np.array(model.gpos0, dtype=float)
     gvel = np.array(model.gvel0, dtype=float)
     free, lin = _free_and_linear(model)
-    if scenario == "human36_free":
-        gpos[lin] = rng.uniform(-0.5, 0.5, int(lin.sum()))
-        t = rng.uniform([-.1, 0., -.1], [.1, .2, .1])
-        r = rng.uniform(-.3, .3, 3)
-        g = int(model.joint_gpos[free[0]])
-        H0 = gpos[g:g + 16].reshape(4, 4)
-        gpos[g:g + 16] = np.dot(np.dot(Hg.transl(*t), Hg.rotzyx(*r)), H0).reshape(-1)
-        gvel[:] = rng.uniform(-1., 1., model.ndof)
-    elif scenario == "human36_contact":
-        gpos[lin] = rng.uniform(-0.1, 0.1, int(lin.sum()))
-        lift = rng.uniform(0.02, 0.07)
-        r = rng.uniform(-.02, .02, 3)
-        g = int(model.joint_gpos[free[0]])
-        H0 = gpos[g:g + 16].reshape(4, 4)
-        # lift is left-multiplied as in tests/test_human36_falling.py:16-18
-        gpos[g:g + 16] = np.dot(Hg.transl(0., lift, 0.),
-                                np.dot(H0, Hg.rotzyx(*r))).reshape(-1)
-    elif scenario == "snake_loop":
+    if scenario == "snake_loop":
         # start (almost) on the closed loop: a large loop error would be
         # corrected within one dt by BallAndSocketConstraint.solve and diverge
         gpos[lin] = SNAKE_QREF + rng.uniform(-1e-3, 1e-3, int(lin.sum()))
@@ -308,6 +367,8 @@ def initial_state(model, scenario, w):
 
 def initial_states(model, scenario, w0, w1):
     """Stacked states of worlds ``w0..w1-1``: gpos (ngpos, W), gvel (ndof, W)."""
+    if scenario in ("human36_free", "human36_contact"):
+        return _human36_states(model, scenario, int(w0), int(w1))
     W = w1 - w0
     gpos = np.empty((model.ngpos, W))
     gvel = np.empty((model.ndof, W))

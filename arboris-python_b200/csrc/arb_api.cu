@@ -75,6 +75,8 @@ static int model_to_device(arb_model* mo, int device) {
   rc |= upload(h.glimdof, &m.glimdof, own);     rc |= upload(h.pd_gpos, &m.pd_gpos, own);
   rc |= upload(h.pd_kp, &m.pd_kp, own);         rc |= upload(h.pd_kd, &m.pd_kd, own);
   rc |= upload(h.pd_qd, &m.pd_qd, own);         rc |= upload(h.pd_c, &m.pd_c, own);
+  rc |= upload(h.pd_dqd, &m.pd_dqd, own);       rc |= upload(h.pd_index, &m.pd_index, own);
+  m.npd = (int)h.pd_dofs.size();
   m.has_pd = h.has_pd; m.gravity = h.gravity; m.nweight = h.nweight;
   if (rc) return -100;
   for (int i = 0; i < 3; ++i) m.up[i] = h.up[i];
@@ -183,6 +185,33 @@ extern "C" int arb_batch_bind_state(arb_batch* b, double* gpos, double* gvel, do
   if (b->model->host.nrows > 0 && !cforce) { arb_set_error("cforce is required when the model has constraints"); return -1; }
   b->d.gpos = gpos; b->d.gvel = gvel; b->d.cforce = cforce;
   return 0;
+}
+
+extern "C" int arb_model_pd_dofs(const arb_model* model, int32_t* dofs, int cap) {
+  if (!model) { arb_set_error("null model"); return -1; }
+  const std::vector<int>& v = model->host.pd_dofs;
+  if (dofs)
+    for (int i = 0; i < (int)v.size() && i < cap; ++i) dofs[i] = v[i];
+  return (int)v.size();
+}
+
+extern "C" int arb_batch_bind_controller_params(arb_batch* b, const double* kp, const double* kd,
+                                                const double* gpos_des, const double* gvel_des) {
+  if (!b) { arb_set_error("null batch"); return -1; }
+  if ((kp || kd || gpos_des || gvel_des) && b->model->host.pd_dofs.empty()) {
+    arb_set_error("the model has no ProportionalDerivativeController"); return -2;
+  }
+  b->d.pkp = kp; b->d.pkd = kd; b->d.pqd = gpos_des; b->d.pdqd = gvel_des;
+  return 0;
+}
+
+/* 1: arb_step runs the fused stages; 0: it runs the four phase kernels (a controller couples dofs
+ * in a way the fused stages do not fold, or "force_phases" is set); *why (optional) names the reason */
+extern "C" int arb_batch_step_path(const arb_batch* b, const char** why) {
+  if (!b) { arb_set_error("null batch"); return -1; }
+  const bool fused = !b->force_phases && arb_fused_supported(b);
+  if (why) *why = fused ? "" : (b->force_phases ? "force_phases option" : b->model->host.fused_why.c_str());
+  return fused ? 1 : 0;
 }
 
 static int check_bound(arb_batch* b) {
@@ -324,7 +353,9 @@ extern "C" int arb_step_host(arb_batch* b, double* h_gpos, double* h_gvel, doubl
   const size_t W = (size_t)b->d.W;
   CUDA_OK(cudaMemcpyAsync(b->d.gpos, h_gpos, sizeof(double) * h.ngpos * W, cudaMemcpyHostToDevice, b->stream));
   CUDA_OK(cudaMemcpyAsync(b->d.gvel, h_gvel, sizeof(double) * h.ndof * W, cudaMemcpyHostToDevice, b->stream));
-  if (h.nrows > 0 && h_cforce)
+  // constraint forces are inputs only where the reference keeps them across steps (ball-and-socket
+  // warm start, constraints.py:164-182); contact and joint-limit rows are reset by every step
+  if (h.nrows > 0 && h_cforce && h.has_warm)
     CUDA_OK(cudaMemcpyAsync(b->d.cforce, h_cforce, sizeof(double) * h.nrows * W, cudaMemcpyHostToDevice, b->stream));
   rc = arb_step(b, dts, nsteps);
   if (rc) return rc;
@@ -348,7 +379,7 @@ extern "C" int arb_step_host_strided(arb_batch* b, double* h_gpos, double* h_gve
   double* host[3] = {h_gpos, h_gvel, h_cforce};
   const int rows[3] = {h.ngpos, h.ndof, h_cforce ? h.nrows : 0};
   for (int a = 0; a < 3; ++a)
-    if (rows[a] > 0)
+    if (rows[a] > 0 && (a < 2 || h.has_warm))     // cforce: host -> device only when it is state
       CUDA_OK(cudaMemcpy2DAsync(dev[a], dp, host[a], hp, dp, rows[a], cudaMemcpyHostToDevice, b->stream));
   rc = arb_step(b, dts, nsteps);
   if (rc) return rc;
@@ -372,6 +403,7 @@ extern "C" int arb_state_copy_host_strided(arb_batch* b, double* h_gpos, double*
   cudaStream_t st = (cudaStream_t)stream;
   for (int a = 0; a < 3; ++a) {
     if (rows[a] <= 0) continue;
+    if (to_device && a == 2 && !h.has_warm) continue;   // cforce is an output only (no ball-and-socket rows)
     if (to_device) CUDA_OK(cudaMemcpy2DAsync(dev[a], dp, host[a], hp, dp, rows[a], cudaMemcpyHostToDevice, st));
     else CUDA_OK(cudaMemcpy2DAsync(host[a], hp, dev[a], dp, dp, rows[a], cudaMemcpyDeviceToHost, st));
   }
@@ -471,6 +503,11 @@ static int check_range(arb_batch* b, const void* out, int64_t w0, int64_t w1, bo
   if (w0 < 0 || w1 > b->d.W || w0 >= w1) { arb_set_error("world range out of bounds"); return -1; }
   if (fused_ok && b->last_fused) return 0;
   if (!b->scratch_dbl) { arb_set_error("nothing to read: no phase call was made on this batch yet"); return -2; }
+  if (b->last_fused) {
+    // the phase scratch is stale by any number of fused steps: refuse instead of returning old data
+    arb_set_error("not formed by the fused step: call arb_update_dynamic / arb_update_controllers first");
+    return -2;
+  }
   return 0;
 }
 
@@ -531,10 +568,6 @@ extern "C" int arb_get_body(arb_batch* b, int which, int body, double* out, int6
                                                                           arb_fused_world_slots(b));
     LAUNCH_CHECK(b);
     return 0;
-  }
-  if (b->last_fused) {
-    arb_set_error("jacobian / djacobian / nleffects are not formed by the fused step: call arb_update_dynamic first");
-    return -2;
   }
   k_get_body<<<(unsigned)((nw + 127) / 128), 128, 0, b->stream>>>(b->m, b->d, which, body, out, w0, nw);
   LAUNCH_CHECK(b);

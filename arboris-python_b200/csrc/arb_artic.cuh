@@ -228,9 +228,24 @@ ARB_D void artic_kinematics(const DevModel& m, const DevBatch& b, int64_t w) {
 }
 
 // generalized force of the (diagonal) PD controllers on dof k        (controllers.py:141-159)
+// Per-world parameters (arb_batch_bind_controller_params) are indexed by WORLD: under a sorted
+// assignment the thread's column w is a slot, its world is perm[w].
+ARB_D int64_t artic_param_world(const DevBatch& b, int64_t w) { return b.perm ? (int64_t)b.perm[w] : w; }
+ARB_D double artic_pd_param(const double* per_world, const double* model, const DevModel& m, const DevBatch& b,
+                            int64_t w, int k) {
+  return per_world ? per_world[(int64_t)m.pd_index[k] * b.W + artic_param_world(b, w)] : model[k];
+}
 ARB_D double artic_tau(const DevModel& m, const DevBatch& b, int64_t w, int k) {
   if (!m.has_pd || m.pd_gpos[k] < 0) return 0.;
-  return m.pd_kp[k] * (m.pd_qd[k] - ST_LD(b.gpos, m.pd_gpos[k])) + m.pd_c[k];
+  const double q = ST_LD(b.gpos, m.pd_gpos[k]);
+  if (!(b.pkp || b.pkd || b.pqd || b.pdqd)) return m.pd_kp[k] * (m.pd_qd[k] - q) + m.pd_c[k];
+  return artic_pd_param(b.pkp, m.pd_kp, m, b, w, k) * (artic_pd_param(b.pqd, m.pd_qd, m, b, w, k) - q) +
+         artic_pd_param(b.pkd, m.pd_kd, m, b, w, k) * artic_pd_param(b.pdqd, m.pd_dqd, m, b, w, k);
+}
+// diagonal impedance of the PD controller on dof k: dt kp + kd
+ARB_D double artic_pd_diag(const DevModel& m, const DevBatch& b, int64_t w, int k, double dt) {
+  if (m.pd_gpos[k] < 0) return 0.;
+  return dt * artic_pd_param(b.pkp, m.pd_kp, m, b, w, k) + artic_pd_param(b.pkd, m.pd_kd, m, b, w, k);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -356,7 +371,7 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
         d += s[r] * t;
         sb += s[r] * beta[r];
       }
-      if (m.has_pd) d += dt * m.pd_kp[k] + m.pd_kd[k];
+      if (m.has_pd) d += artic_pd_diag(m, b, w, k, dt);
       if (!(fabs(d) > 0.)) ok = false;
       const double dinv = 1. / d;
 #pragma unroll

@@ -212,10 +212,14 @@ static int fused_state_sync(arb_batch* b, bool gather) {
     k_status_merge<<<(unsigned)((W + 255) / 256), 256, 0, b->stream>>>(b->d.status, f->pstatus, perm, W);
     b->launches += 1;
   }
+  const cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { arb_set_error(std::string("state copy launch: ") + cudaGetErrorString(e)); return -101; }
   return 0;
 }
 
 int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
+  for (int s = 0; s < nsteps; ++s)       // before anything is enqueued: a bad dt leaves the state untouched
+    if (!(dts[s] > 0)) { arb_set_error("dt must be > 0"); return -3; }
   int rc = ensure_fused_scratch(b);
   if (rc) return rc;
   FusedState* f = b->fused;
@@ -223,8 +227,6 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
   const int64_t W = b->d.W;
   const unsigned g = (unsigned)((W + FUSED_THREADS - 1) / FUSED_THREADS);
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  if (b->time_stages)
-    for (int i = 0; i < 4; ++i) CUDA_OKF(cudaEventCreate(&ev[i]));
   if (f->sorted && b->sort_period <= 0) {       // sorting switched off: back to the identity
     k_iota<<<(unsigned)((W + 255) / 256), 256, 0, b->stream>>>(f->perm[f->cur], W);
     f->sorted = false;
@@ -239,30 +241,54 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
     d.cforce = d.gvel + (int64_t)h.ndof * W;
     d.status = f->pstatus;
   };
+  bool priv_valid = false;
+  // every exit goes through here: the live state goes back to the caller's arrays (the steps
+  // already enqueued are not lost when a later call fails) and the timing events are released
+  auto leave = [&](int code) {
+    if (f->sorted && priv_valid) {
+      const int rs = fused_state_sync(b, false);
+      if (code == 0) code = rs;
+    }
+    for (int i = 0; i < 4; ++i)
+      if (ev[i]) cudaEventDestroy(ev[i]);
+    return code;
+  };
+#define CUDA_OKL(call)                                                            \
+  do {                                                                            \
+    cudaError_t e_ = (call);                                                      \
+    if (e_ != cudaSuccess) {                                                      \
+      arb_set_error(std::string(#call) + ": " + cudaGetErrorString(e_));          \
+      return leave(-100);                                                         \
+    }                                                                             \
+  } while (0)
+  if (b->time_stages)
+    for (int i = 0; i < 4; ++i) CUDA_OKL(cudaEventCreate(&ev[i]));
   // (a call whose first step re-sorts anyway does not gather first: the caller's arrays are the
   // state at that point -- one gather and one scatter less per sort for callers that step once per
   // call, like the end-to-end pipeline)
   const bool sort_first = nsteps > 0 && f->perm[0] != nullptr && b->sort_period > 0 && f->steps > 0 &&
                           (f->steps % b->sort_period) == 0;
-  bool priv_valid = false;
   if (f->sorted && !sort_first) {
     rc = fused_state_sync(b, true);
-    if (rc) return rc;
+    if (rc) return leave(rc);
     point_at_private();
     priv_valid = true;
   }
   for (int s = 0; s < nsteps; ++s) {
     const double dt = dts[s];
-    if (!(dt > 0)) { arb_set_error("dt must be > 0"); return -3; }
     if (f->perm[0] != nullptr && b->sort_period > 0 && f->steps > 0 && (f->steps % b->sort_period) == 0) {
       // re-assign worlds to threads by the key of the previous step, DESCENDING: the CTAs of the
       // worlds with the most contact work are dispatched first and the grid's tail is made of the
       // cheap ones (stable: ties keep their order).  Done BEFORE the step, so that after a step the scratch read-backs
       // (arb_get_constraint) still see the assignment the step ran with.
-      if (f->sorted && priv_valid) fused_state_sync(b, false);
+      if (f->sorted && priv_valid) {
+        priv_valid = false;
+        rc = fused_state_sync(b, false);
+        if (rc) return leave(rc);
+      }
       const int nb = b->m.nc < 32 ? b->m.nc : 32;
       const int c = f->cur;
-      CUDA_OKF(cub::DeviceRadixSort::SortPairsDescending(f->cub_tmp, f->cub_bytes, f->key[c], f->key[c ^ 1], f->perm[c],
+      CUDA_OKL(cub::DeviceRadixSort::SortPairsDescending(f->cub_tmp, f->cub_bytes, f->key[c], f->key[c ^ 1], f->perm[c],
                                                f->perm[c ^ 1], (int)W, 0, 2 * nb, b->stream));
       f->cur = c ^ 1;
       b->d.perm = d.perm = f->perm[f->cur];
@@ -270,7 +296,8 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
       f->inv_valid = false;
       f->sorted = true;
       b->launches += 1;
-      fused_state_sync(b, true);
+      rc = fused_state_sync(b, true);
+      if (rc) return leave(rc);
       point_at_private();
       priv_valid = true;
     }
@@ -290,7 +317,7 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
     ++f->steps;
     if (ev[0]) {   // diagnostic mode: per-stage device time of this step
       cudaEventRecord(ev[3], b->stream);
-      CUDA_OKF(cudaEventSynchronize(ev[3]));
+      CUDA_OKL(cudaEventSynchronize(ev[3]));
       for (int i = 0; i < 3; ++i) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
@@ -299,9 +326,9 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
       b->stage_ms[3] += 1.;
     }
   }
-  if (f->sorted) fused_state_sync(b, false);
-  for (int i = 0; i < 4; ++i)
-    if (ev[i]) cudaEventDestroy(ev[i]);
+#undef CUDA_OKL
+  rc = leave(0);
+  if (rc) return rc;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { arb_set_error(std::string("kernel launch: ") + cudaGetErrorString(e)); return -101; }
   return 0;

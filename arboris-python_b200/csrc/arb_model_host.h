@@ -18,8 +18,10 @@ struct HostModel {
   int ngen = 0, ngrows = 0;
   // articulated-body tables
   std::vector<int> dofjoint, jhaschild, jaccfirst, jmark, jmarkfirst, jmarkchild, glimdof, pd_gpos;
+  std::vector<int> pd_index, pd_dofs;   // per-world controller parameters: dof -> row (or -1), row -> dof
+  int has_warm = 0;                     // some constraint force is state across steps (ball and socket)
   std::vector<int> jchild0, jsib;   // first child joint of body j+1 / next sibling joint (-1: none), ascending
-  std::vector<double> pd_kp, pd_kd, pd_qd, pd_c;
+  std::vector<double> pd_kp, pd_kd, pd_qd, pd_c, pd_dqd;
   int has_pd = 0, nweight = 0;
   double gravity = 0.;
   int fused_ok = 1;            // 0: a controller couples dofs in a way the fused step does not support
@@ -110,9 +112,13 @@ static inline int build_host_model(const arb_model_desc* d, HostModel& m, std::s
     if (m.crow[c] != rows) { err = "constraint rows are not contiguous"; return -3; }
     rows += arb_cons_ndol(t);
     const int* ci = &m.cint[ARB_CONS_NINT * c];
+    if (t == ARB_CONS_BALL_SOCKET) m.has_warm = 1;
     if (t == ARB_CONS_JOINT_LIMITS) {
       if (ci[0] < 0 || ci[0] >= nj || arb_joint_ndof(m.jtype[ci[0]]) != 1) {
         err = "JointLimits needs a 1-dof joint"; return -3;
+      }
+      if (ci[1] != m.jdof[ci[0]] || ci[2] != m.jgpos[ci[0]]) {
+        err = "JointLimits dof / gpos index does not match its joint"; return -3;
       }
     } else if (ci[0] < 0 || ci[0] > nj || ci[1] < 0 || ci[1] > nj) {
       err = "constraint body index out of range"; return -3;
@@ -125,8 +131,21 @@ static inline int build_host_model(const arb_model_desc* d, HostModel& m, std::s
   m.aint.assign(d->ctrl_int, d->ctrl_int + 4 * m.na);
   m.adbl.assign(d->ctrl_dbl, d->ctrl_dbl + 4 * m.na);
   if (d->nblob > 0) m.ablob.assign(d->ctrl_blob, d->ctrl_blob + d->nblob);
-  for (int a = 0; a < m.na; ++a)
+  for (int a = 0; a < m.na; ++a) {
     if (m.atype[a] != ARB_CTRL_WEIGHT && m.atype[a] != ARB_CTRL_PD) { err = "unknown controller type"; return -4; }
+    if (m.atype[a] != ARB_CTRL_PD) continue;
+    // PD blob: {dof map[m], gpos map[m], kp[m*m], kd[m*m], gpos_des[m], gvel_des[m]}
+    const long mm = m.aint[4 * a], off = m.aint[4 * a + 1];
+    if (mm < 0 || off < 0 || off + 4 * mm + 2 * mm * mm > (long)d->nblob) {
+      err = "PD controller blob out of range"; return -4;
+    }
+    for (long i = 0; i < mm; ++i) {
+      const double kd_ = m.ablob[off + i], kg = m.ablob[off + mm + i];
+      if (!(kd_ >= 0. && kd_ < m.ndof && kd_ == (double)(int)kd_) || !(kg >= 0. && kg < m.ngpos && kg == (double)(int)kg)) {
+        err = "PD controller dof / gpos index out of range"; return -4;
+      }
+    }
+  }
   for (int i = 0; i < 3; ++i) m.up[i] = d->up[i];
   // fused-path tables
   m.dofbody.assign(m.ndof, 0);
@@ -218,7 +237,8 @@ static inline int build_host_model(const arb_model_desc* d, HostModel& m, std::s
     }
   }
   m.pd_kp.assign(m.ndof, 0.); m.pd_kd.assign(m.ndof, 0.); m.pd_qd.assign(m.ndof, 0.);
-  m.pd_c.assign(m.ndof, 0.); m.pd_gpos.assign(m.ndof, -1);
+  m.pd_c.assign(m.ndof, 0.); m.pd_dqd.assign(m.ndof, 0.); m.pd_gpos.assign(m.ndof, -1);
+  m.pd_index.assign(m.ndof > 0 ? m.ndof : 1, -1);
   for (int a = 0; a < m.na; ++a) {
     if (m.atype[a] == ARB_CTRL_WEIGHT) { m.gravity += m.adbl[4 * a]; m.nweight++; continue; }
     m.has_pd = 1;
@@ -237,11 +257,14 @@ static inline int build_host_model(const arb_model_desc* d, HostModel& m, std::s
           m.fused_why = "PD controller with off-diagonal gains";
         }
       if (m.pd_gpos[k] >= 0) { m.fused_ok = 0; m.fused_why = "two PD controllers on one dof"; }
+      if (m.pd_index[k] < 0) m.pd_index[k] = (int)m.pd_dofs.size();   // (a second controller on the dof shares the row)
+      m.pd_dofs.push_back(k);
       m.pd_gpos[k] = (int)gmap[i];
       m.pd_kp[k] = kp[i * mm + i];
       m.pd_kd[k] = kd[i * mm + i];
       m.pd_qd[k] = qd[i];
       m.pd_c[k] = kd[i * mm + i] * dqd[i];
+      m.pd_dqd[k] = dqd[i];
     }
   }
   return 0;

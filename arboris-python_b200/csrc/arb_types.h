@@ -70,8 +70,10 @@ struct DevModel {
   const int *glimdof;                          // [ngrows - 6 ngen] dof of each joint-limit generator row
   // diagonal PD controllers folded per dof: tau = kp (qd - q) + c, Z[k][k] += dt kp + kd
   int has_pd;
-  const double *pd_kp, *pd_kd, *pd_qd, *pd_c;  // [ndof]
+  const double *pd_kp, *pd_kd, *pd_qd, *pd_c, *pd_dqd;  // [ndof]
   const int *pd_gpos;                          // [ndof] gpos index of the dof (or -1)
+  const int *pd_index;                         // [ndof] row of the dof in the per-world controller parameters (or -1)
+  int npd;                                     // dofs driven by PD controllers (rows of the per-world parameters)
   double gravity;                              // sum of the WeightControllers' gravity
   int nweight;
 };
@@ -81,6 +83,9 @@ struct DevModel {
 struct DevBatch {
   int64_t W;
   double *gpos, *gvel, *cforce;        // state (bound)
+  // per-world PD controller parameters, [npd][W] by WORLD index (arb_batch_bind_controller_params);
+  // nullptr: the model's value for every world
+  const double *pkp, *pkd, *pqd, *pdqd;
   // update_dynamic outputs
   double *pose;      // [nj][12]
   double *twist;     // [nj][6]

@@ -290,14 +290,30 @@ ARB_D void world_update_controllers(const DevModel& m, const DevBatch& b, int64_
       const double* kd = kp + mm * mm;
       const double* qd = kd + mm * mm;
       const double* dqd = qd + mm;
+      // per-world parameters (arb_batch_bind_controller_params): rows prow + i of [npd][W] arrays
+      // replace gpos_des, gvel_des and the DIAGONAL gains of this controller
+      int prow = 0;
+      for (int a2 = 0; a2 < a; ++a2)
+        if (m.atype[a2] == ARB_CTRL_PD) prow += m.aint[4 * a2];
       for (int i = 0; i < mm; ++i) {
         double t = 0.;
-        for (int j = 0; j < mm; ++j) t += kp[i * mm + j] * (qd[j] - AT(b.gpos, (int)gmap[j]));
+        for (int j = 0; j < mm; ++j) {
+          const double kpij = (i == j && b.pkp) ? b.pkp[(int64_t)(prow + j) * W + w] : kp[i * mm + j];
+          const double qdj = b.pqd ? b.pqd[(int64_t)(prow + j) * W + w] : qd[j];
+          t += kpij * (qdj - AT(b.gpos, (int)gmap[j]));
+        }
         double t2 = 0.;
-        for (int j = 0; j < mm; ++j) t2 += kd[i * mm + j] * dqd[j];
+        for (int j = 0; j < mm; ++j) {
+          const double kdij = (i == j && b.pkd) ? b.pkd[(int64_t)(prow + j) * W + w] : kd[i * mm + j];
+          const double dqdj = b.pdqd ? b.pdqd[(int64_t)(prow + j) * W + w] : dqd[j];
+          t2 += kdij * dqdj;
+        }
         AT(b.gforce, (int)dofs[i]) += t + t2;
-        for (int j = 0; j < mm; ++j)
-          AT(b.Z, (int)dofs[i] * n + (int)dofs[j]) -= -(dt * kp[i * mm + j] + kd[i * mm + j]);
+        for (int j = 0; j < mm; ++j) {
+          const double kpij = (i == j && b.pkp) ? b.pkp[(int64_t)(prow + j) * W + w] : kp[i * mm + j];
+          const double kdij = (i == j && b.pkd) ? b.pkd[(int64_t)(prow + j) * W + w] : kd[i * mm + j];
+          AT(b.Z, (int)dofs[i] * n + (int)dofs[j]) -= -(dt * kpij + kdij);
+        }
       }
     }
   }

@@ -23,7 +23,8 @@
  *      gvel  : World._gvel                          (core.py:626-629)
  *      cforce: every constraint's _force, stacked in registration order
  *              (constraints.py:52,153,422); only BallAndSocketConstraint rows
- *              are read as state (warm start), the others are outputs.
+ *              are read as state (warm start), the others are outputs (the host-buffer
+ *              entry points copy cforce host -> device only for models with such rows).
  *  - All work is enqueued on the batch's stream and is asynchronous w.r.t. the
  *    host unless stated.  One batch is driven by one host thread at a time.
  */
@@ -150,6 +151,24 @@ int arb_batch_set_option(arb_batch *batch, const char *name, int value);
 
 /* caller-owned DEVICE state, layouts in the header comment */
 int arb_batch_bind_state(arb_batch *batch, double *gpos, double *gvel, double *cforce);
+
+/* Per-world parameters of the ProportionalDerivativeControllers (controllers.py:63-159: kp, kd,
+ * gpos_des, gvel_des; used at :141-159).  The reference keeps them on the controller object of ONE
+ * world; a batch may give every world its own.  DEVICE arrays [npd][W], world index fastest, caller-
+ * owned like the state; row p belongs to the p-th controlled dof, counting the controllers in
+ * registration order and each controller's dofs in its own order (arb_model_pd_dofs lists them).
+ * kp / kd rows are the DIAGONAL gains of that dof (off-diagonal gains stay the model's).  A NULL
+ * pointer means "the model's value for every world"; all NULL unbinds.  Read by every later
+ * arb_update_controllers / arb_step. */
+int arb_batch_bind_controller_params(arb_batch *batch, const double *kp, const double *kd,
+                                     const double *gpos_des, const double *gvel_des);
+/* dof of each row of those arrays: writes min(npd, cap) entries, returns npd (dofs may be NULL) */
+int arb_model_pd_dofs(const arb_model *model, int32_t *dofs, int cap);
+/* which implementation arb_step runs for this batch: 1 = the fused stages, 0 = the four phase
+ * kernels (a PD controller with off-diagonal gains or two controllers on one dof -- Z then has
+ * entries the per-dof articulated elimination does not fold -- or the "force_phases" option).
+ * *why (may be NULL) receives a static string naming the reason. */
+int arb_batch_step_path(const arb_batch *batch, const char **why);
 
 /* replaces World.update_dynamic (core.py:682-734; Body.update_dynamic :1272-1315) */
 int arb_update_dynamic(arb_batch *batch);

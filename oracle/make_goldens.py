@@ -86,12 +86,18 @@ def get_gpos(world, model):
     return out
 
 
-def run_reference(scenario, world_ids, nsteps, dt, full_steps=(0,), reset_bs=True):
-    """Step the real reference; return dict of stacked per-step records."""
+def run_reference(scenario, world_ids, nsteps, dt, full_steps=(0,), reset_bs=True, keep=None,
+                  fields=None, per_world=None):
+    """Step the real reference; return dict of stacked per-step records.
+    ``keep``: steps whose records are stored (default all) -- long free-running trajectories keep a
+    few checkpoints only (``kept_steps`` in the output).  ``fields``: subset of the per-step
+    records to store.  ``per_world(world, wid)``: hook run before a world is stepped (sets
+    per-world controller parameters on the reference's own objects)."""
     w = scenarios.BUILDERS[scenario](reference=True)
     model = flatten(w)
-    rec = {k: [] for k in ("gpos", "gvel", "gforce_ctrl", "gforce", "active",
-                           "branch", "cforce", "sdist")}
+    names = ("gpos", "gvel", "gforce_ctrl", "gforce", "active", "branch", "cforce", "sdist")
+    rec = {k: [] for k in names if fields is None or k in fields}
+    keepset = None if keep is None else set(int(k) for k in keep)
     full = {k: [] for k in ("mass", "nleffects", "viscosity", "impedance",
                             "admittance")}
     gpos_in, gvel_in = [], []
@@ -101,15 +107,19 @@ def run_reference(scenario, world_ids, nsteps, dt, full_steps=(0,), reset_bs=Tru
         set_state(w, model, gpos, gvel)
         for c in cons:
             c._force[:] = 0.
+        if per_world is not None:
+            per_world(w, wid)
         gpos_in.append(gpos)
         gvel_in.append(gvel)
         r = {k: [] for k in rec}
         fl = {k: [] for k in full}
         for s in range(nsteps):
             _branch_log.clear()
+            kept = keepset is None or s in keepset
             w.update_dynamic()
             w.update_controllers(dt)
-            r["gforce_ctrl"].append(w._gforce.copy())
+            if kept and "gforce_ctrl" in r:
+                r["gforce_ctrl"].append(w._gforce.copy())
             if s in full_steps:
                 fl["mass"].append(w.mass.copy())
                 fl["nleffects"].append(w.nleffects.copy())
@@ -117,21 +127,26 @@ def run_reference(scenario, world_ids, nsteps, dt, full_steps=(0,), reset_bs=Tru
                 fl["impedance"].append(w._impedance.copy())
                 fl["admittance"].append(w._admittance.copy())
             w.update_constraints(dt)
-            r["gforce"].append(w._gforce.copy())
-            r["active"].append([1 if (c.is_enabled() and c.is_active()) else 0 for c in cons])
-            r["branch"].append([_branch_log.get(id(c), 0) for c in cons])
-            cf = np.zeros(model.nrows)
-            sd = np.zeros(len(cons))
-            for k, c in enumerate(cons):
-                r0 = int(model.cons_row[k])
-                f = np.asarray(c._force, dtype=float).reshape(-1)
-                cf[r0:r0 + f.size] = f
-                sd[k] = getattr(c, "_sdist", 0.) or 0.
-            r["cforce"].append(cf)
-            r["sdist"].append(sd)
+            if kept:
+                cf = np.zeros(model.nrows)
+                sd = np.zeros(len(cons))
+                for k, c in enumerate(cons):
+                    r0 = int(model.cons_row[k])
+                    f = np.asarray(c._force, dtype=float).reshape(-1)
+                    cf[r0:r0 + f.size] = f
+                    sd[k] = getattr(c, "_sdist", 0.) or 0.
+                vals = {"gforce": w._gforce.copy(),
+                        "active": [1 if (c.is_enabled() and c.is_active()) else 0 for c in cons],
+                        "branch": [_branch_log.get(id(c), 0) for c in cons], "cforce": cf, "sdist": sd}
+                for k2, v2 in vals.items():
+                    if k2 in r:
+                        r[k2].append(v2)
             w.integrate(dt)
-            r["gvel"].append(w._gvel.copy())
-            r["gpos"].append(get_gpos(w, model))
+            if kept:
+                if "gvel" in r:
+                    r["gvel"].append(w._gvel.copy())
+                if "gpos" in r:
+                    r["gpos"].append(get_gpos(w, model))
         for k in rec:
             rec[k].append(np.array(r[k]))
         for k in full:
@@ -143,14 +158,17 @@ def run_reference(scenario, world_ids, nsteps, dt, full_steps=(0,), reset_bs=Tru
     out["world_ids"] = np.array(world_ids)
     out["full_steps"] = np.array(full_steps)
     out["dt"] = np.array(dt)
-    out["active"] = out["active"].astype(np.int8)
-    out["branch"] = out["branch"].astype(np.int8)
+    out["kept_steps"] = np.array(sorted(keepset) if keepset is not None else np.arange(nsteps))
+    for k in ("active", "branch"):
+        if k in out:
+            out[k] = out[k].astype(np.int8)
     return model, out
 
 
-def save(name, model, out):
-    model.save(os.path.join(GOLD, "model_%s.npz" % name))
-    np.savez_compressed(os.path.join(GOLD, "traj_%s.npz" % name), **out)
+def save(name, model, out, prefix="traj", with_model=True):
+    if with_model:
+        model.save(os.path.join(GOLD, "model_%s.npz" % name))
+    np.savez_compressed(os.path.join(GOLD, "%s_%s.npz" % (prefix, name)), **out)
     print("wrote", name, {k: v.shape for k, v in out.items() if v.ndim > 1})
 
 
@@ -208,6 +226,67 @@ def main():
     print("  limits branches seen:", np.unique(o["branch"], return_counts=True))
     balls()
     zoo()
+    contact64()
+    free_running()
+    zoo_pd()
+
+
+STATE_FIELDS = ("gpos", "gvel", "cforce", "active", "branch")
+
+
+def contact64():
+    """SURVEY.md 8(d) config 3 parity subset: 64 falling humanoids, the reference's own
+    free-running trajectory (state, forces, active sets, branches after every step)."""
+    m, o = run_reference("human36_contact", list(range(64)), 120, 1e-3, full_steps=(), fields=STATE_FIELDS)
+    save("human36_contact64", m, o, with_model=False)
+    print("  contact64 branches:", np.unique(o["branch"], return_counts=True))
+
+
+def free_running():
+    """north_star: trajectories within 1e-6 after 1000 steps.  1000 free-running steps of the
+    real reference on configs 2 and 4, checkpoints every 100 steps."""
+    keep = list(range(99, 1000, 100))
+    m, o = run_reference("human36_free", [0, 1, 2, 3], 1000, 1e-3, full_steps=(), keep=keep,
+                         fields=("gpos", "gvel"))
+    save("human36_free", m, o, prefix="free", with_model=False)
+    m, o = run_reference("snake_loop", [0, 1], 1000, 1e-3, full_steps=(), keep=keep,
+                         fields=("gpos", "gvel", "cforce"))
+    save("snake_loop", m, o, prefix="free", with_model=False)
+
+
+def pd_params(wid, npd):
+    """Per-world PD parameters of the zoo_pd fixture (rows as arb_model_pd_dofs)."""
+    rng = np.random.default_rng(777 + wid)
+    return {"kp": rng.uniform(5., 40., npd), "kd": rng.uniform(.3, 3., npd),
+            "gpos_des": rng.uniform(-.3, .3, npd), "gvel_des": rng.uniform(-.2, .2, npd)}
+
+
+def zoo_pd():
+    """per-world controller parameters.  Every world of the zoo gets its own
+    kp, kd (diagonal), gpos_des, gvel_des on the reference's ProportionalDerivativeController
+    objects (controllers.py:113-131) before it is stepped."""
+    import arboris.controllers as rctrl
+    stash = {}
+
+    def hook(world, wid):
+        pds = [c for c in world._controllers if isinstance(c, rctrl.ProportionalDerivativeController)]
+        npd = sum(c._cndof for c in pds)
+        p = pd_params(wid, npd)
+        stash[wid] = p
+        r = 0
+        for c in pds:
+            n = c._cndof
+            c.kp = np.diag(p["kp"][r:r + n])
+            c.kd = np.diag(p["kd"][r:r + n])
+            c.gpos_des = p["gpos_des"][r:r + n].copy()
+            c.gvel_des = p["gvel_des"][r:r + n].copy()
+            r += n
+    ids = [0, 1, 2, 3]
+    m, o = run_reference("zoo", ids, 200, 1e-3, full_steps=(0, 100), per_world=hook)
+    for k in ("kp", "kd", "gpos_des", "gvel_des"):
+        o["pd_" + k] = np.array([stash[w][k] for w in ids]).T        # (npd, W)
+    save("zoo_pd", m, o, with_model=False)
+    print("  zoo_pd: limit active in", int(o["active"].sum()), "world-steps")
 
 
 def zoo():
@@ -228,7 +307,10 @@ def balls():
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] in ("balls", "zoo"):
-        {"balls": balls, "zoo": zoo}[sys.argv[1]]()
+    only = {"balls": balls, "zoo": zoo, "contact64": contact64, "free_running": free_running,
+            "zoo_pd": zoo_pd}
+    if len(sys.argv) > 1 and all(a in only for a in sys.argv[1:]):
+        for a in sys.argv[1:]:
+            only[a]()
     else:
         main()

@@ -16,6 +16,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "reference: needs the read-only reference tree at /root/reference")
 
 
+def pytest_collection_modifyitems(config, items):
+    """GPU tests are SKIPPED (not errors) on a machine without a CUDA device, so that a plain
+    ``pytest tests`` works there too."""
+    gpu_items = [it for it in items if it.get_closest_marker("gpu") is not None]
+    if not gpu_items:
+        return
+    try:
+        import torch
+        have = torch.cuda.is_available()
+    except Exception:
+        have = False
+    if not have:
+        skip = pytest.mark.skip(reason="needs a CUDA device")
+        for it in gpu_items:
+            it.add_marker(skip)
+
+
 def load_golden(name):
     import numpy as np
     from arboris_b200.flatten import FlatModel

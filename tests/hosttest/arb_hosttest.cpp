@@ -31,6 +31,7 @@ static DevModel view(const HostModel& h) {
   m.jchild0 = h.jchild0.data(); m.jsib = h.jsib.data();
   m.glimdof = h.glimdof.data(); m.pd_gpos = h.pd_gpos.data(); m.pd_kp = h.pd_kp.data();
   m.pd_kd = h.pd_kd.data(); m.pd_qd = h.pd_qd.data(); m.pd_c = h.pd_c.data();
+  m.pd_dqd = h.pd_dqd.data(); m.pd_index = h.pd_index.data(); m.npd = (int)h.pd_dofs.size();
   m.has_pd = h.has_pd; m.gravity = h.gravity; m.nweight = h.nweight;
   return m;
 }
@@ -73,6 +74,10 @@ void ht_set_coop(void* p, int v) { ((HostBatch*)p)->coop = v; }
 void ht_bind(void* p, double* gpos, double* gvel, double* cforce) {
   HostBatch* hb = (HostBatch*)p;
   hb->b.gpos = gpos; hb->b.gvel = gvel; hb->b.cforce = cforce;
+}
+void ht_bind_params(void* p, const double* kp, const double* kd, const double* qd, const double* dqd) {
+  HostBatch* hb = (HostBatch*)p;
+  hb->b.pkp = kp; hb->b.pkd = kd; hb->b.pqd = qd; hb->b.pdqd = dqd;
 }
 void ht_update_dynamic(void* p) {
   HostBatch* hb = (HostBatch*)p;

@@ -77,6 +77,12 @@ class HostBatch(object):
         n = self.L.ht_aligned(self.h, g.ctypes.data, c.ctypes.data)
         return g[:n].copy(), c[:len(self.model.cons_type)].copy()
 
+    def bind_params(self, kp, kd, qd, dqd):
+        """per-world PD parameters, (npd, W) C-contiguous arrays (kept alive by the caller)"""
+        self._params = [np.ascontiguousarray(a, dtype=np.float64) for a in (kp, kd, qd, dqd)]
+        self.L.ht_bind_params.argtypes = [C.c_void_p] * 5
+        self.L.ht_bind_params(self.h, *[a.ctypes.data for a in self._params])
+
     def update_dynamic(self):
         self.L.ht_update_dynamic(self.h)
 

@@ -24,7 +24,8 @@ def rel(a, b):
 @pytest.fixture(scope="module")
 def env():
     import torch
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    if not torch.cuda.is_available():
+        pytest.skip("GPU tests need a CUDA device")
     from arboris_b200 import scenarios
     from arboris_b200.batch import BatchedWorld
     from arboris_b200.flatten import flatten
@@ -65,19 +66,33 @@ def _oracle_steps(model, gpos, gvel, cforce, nsteps):
     return o
 
 
-def _fused_vs_phases(bw, torch, tol):
-    """one step from the current state by both paths; returns the state after the fused step"""
+def _fused_vs_phases(bw, torch, tol, tag=""):
+    """One step from the current state by both paths (two independent algorithms: the explicit
+    42x42 LU inverse + assembled Delassus operator, and the articulated elimination + generator-
+    space Gauss-Seidel).  north_star's 1e-10 is asserted for the bulk of the batch (99 %); the
+    worst world of tens of thousands is bounded by `tol` and its conditioning is printed: the
+    difference of two backward-stable solves of Z x = b is ~ cond(Z) eps each (cond(Z) ~ 1e5 here),
+    and a contact world adds the conditioning of its Delassus blocks.  Returns the active sets."""
     g0, v0, f0 = bw.gpos.clone(), bw.gvel.clone(), bw.cforce.clone()
     bw.set_option("force_phases", 1)
     bw.step(DT, 1)
     gp, vp, fp = bw.gpos.clone(), bw.gvel.clone(), bw.cforce.clone()
     act_p = bw.constraints("active").clone()
+    Zall = bw.matrix("impedance")            # of the state both paths start from
     bw.set_option("force_phases", 0)
     bw.gpos.copy_(g0); bw.gvel.copy_(v0); bw.cforce.copy_(f0)
     bw.step(DT, 1)
     scale = vp.abs().amax(0).clamp_min(1e-3)
-    dv = ((bw.gvel - vp).abs().amax(0)/scale).max().item()
+    dvw = (bw.gvel - vp).abs().amax(0)/scale
+    dv = dvw.max().item()
     dg = (bw.gpos - gp).abs().max().item()
+    q99 = torch.quantile(dvw[torch.randperm(dvw.numel(), device=dvw.device)[:100000]], 0.99).item()
+    worst = int(dvw.argmax())
+    condZ = float(torch.linalg.cond(Zall[worst]))
+    del Zall
+    print("fused vs phases %s: max rel dv %.3g (world %d, cond(Z) %.3g, active %d), 99%% quantile %.3g, "
+          "max |dq| %.3g" % (tag, dv, worst, condZ, int(act_p[worst].sum()), q99, dg))
+    assert q99 < 1e-10, q99
     assert dv < tol, dv
     assert dg < tol, dg
     return act_p
@@ -131,7 +146,7 @@ def test_config3_human36_contact_16384(env):
     v1 = bw.gvel[:, :3].cpu().numpy()
     for w in range(3):
         o = _oracle_steps(model, g0[:, w], v0[:, w], None, 1)
-        assert rel(v1[:, w], o.gvel) < 1e-9
+        assert rel(v1[:, w], o.gvel) < 1e-10
     _status_ok(bw)
 
 

@@ -22,7 +22,8 @@ def rel(a, b):
 @pytest.fixture(scope="module")
 def torch_cuda():
     import torch
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    if not torch.cuda.is_available():
+        pytest.skip("GPU tests need a CUDA device")
     return torch
 
 
@@ -47,6 +48,10 @@ def test_phases_vs_real_reference(torch_cuda, name):
         bw.set_state(gpos, gvel, cf)
         bw.update_dynamic()
         bw.update_controllers(dt)
+        # a10: World._gforce after the controllers (WeightController / PD generalized force)
+        if np.abs(tr["gforce_ctrl"][:, s]).max() > 0:
+            worst["gforce_ctrl"] = max(worst.get("gforce_ctrl", 0),
+                                       rel(bw.gforce().cpu().numpy(), tr["gforce_ctrl"][:, s]))
         if s in fs:
             i = fs.index(s)
             for k in ("mass", "nleffects", "impedance", "admittance"):
@@ -56,9 +61,8 @@ def test_phases_vs_real_reference(torch_cuda, name):
             a = bw.constraints("active").cpu().numpy()
             br = bw.constraints("branch").cpu().numpy()
             flips += int((a != tr["active"][:, s]).sum()) + int((br*a != tr["branch"][:, s]).sum())
-            if name != "ball_socket":
-                worst["cforce"] = max(worst.get("cforce", 0),
-                                      rel(bw.cforce.cpu().numpy().T[:, :model.nrows], tr["cforce"][:, s]))
+            worst["cforce"] = max(worst.get("cforce", 0),
+                                  rel(bw.cforce.cpu().numpy().T[:, :model.nrows], tr["cforce"][:, s]))
         bw.integrate(dt)
         g, v, _ = bw.get_state()
         worst["gvel"] = max(worst.get("gvel", 0), rel(v.T, tr["gvel"][:, s]))
@@ -97,7 +101,7 @@ def test_fused_step_vs_real_reference(torch_cuda, name):
                 worst["sdist"] = max(worst.get("sdist", 0), np.abs(sd - tr["sdist"][:, s][:, :8]).max()*1e-2)
         worst["gvel"] = max(worst.get("gvel", 0), rel(v.T, tr["gvel"][:, s]))
         worst["gpos"] = max(worst.get("gpos", 0), rel(g.T, tr["gpos"][:, s]))
-        if model.nrows and name != "ball_socket":
+        if model.nrows:
             worst["cforce"] = max(worst.get("cforce", 0), rel(f.T, tr["cforce"][:, s]))
         gpos, gvel = tr["gpos"][:, s].T.copy(), tr["gvel"][:, s].T.copy()
         if model.nrows:
@@ -223,3 +227,187 @@ def test_cooperative_gauss_seidel_is_bit_identical_to_per_lane(torch_cuda):
     for a, b in zip(out[0], out[1]):
         assert np.array_equal(a, b)
     assert np.abs(out[0][2]).max() > 0        # contact forces are present
+
+
+# ---------------------------------------------------------------------------------------------
+# round 2: SURVEY.md 8(d) config 3 parity subset (64 worlds), free-running trajectories,
+# per-world controller parameters, body Jacobians on the GPU
+# ---------------------------------------------------------------------------------------------
+def _load_extra(model_name, file_name):
+    import os
+    from conftest import GOLDEN
+    from arboris_b200.flatten import FlatModel
+    model = FlatModel.load(os.path.join(GOLDEN, "model_%s.npz" % model_name))
+    with np.load(os.path.join(GOLDEN, file_name)) as z:
+        return model, {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize("path", ["fused", "phases"])
+def test_contact64_teacher_forced(torch_cuda, path):
+    """64 falling humanoids (SURVEY.md 8(d) config 3): every step from the REAL reference's state;
+    active sets and branches bit-exact, velocities / positions / forces within 1e-10."""
+    model, tr = _load_extra("human36_contact", "traj_human36_contact64.npz")
+    dt = float(tr["dt"])
+    W, T = tr["gpos"].shape[:2]
+    bw = _batch(model, W)
+    if path == "phases":
+        bw.set_option("force_phases", 1)
+        T = min(T, 60)
+    gpos, gvel = tr["gpos_in"].T.copy(), tr["gvel_in"].T.copy()
+    cf = np.zeros((model.nrows, W))
+    worst, flips, nact = {}, 0, 0
+    for s in range(T):
+        bw.set_state(gpos, gvel, cf)
+        bw.step(dt, 1)
+        g, v, f = bw.get_state()
+        a = bw.constraints("active").cpu().numpy()
+        br = bw.constraints("branch").cpu().numpy()
+        flips += int((a != tr["active"][:, s]).sum()) + int((br*a != tr["branch"][:, s]).sum())
+        nact += int(a.sum())
+        worst["gvel"] = max(worst.get("gvel", 0), rel(v.T, tr["gvel"][:, s]))
+        worst["gpos"] = max(worst.get("gpos", 0), rel(g.T, tr["gpos"][:, s]))
+        worst["cforce"] = max(worst.get("cforce", 0), rel(f.T, tr["cforce"][:, s]))
+        gpos, gvel, cf = tr["gpos"][:, s].T.copy(), tr["gvel"][:, s].T.copy(), tr["cforce"][:, s].T.copy()
+    assert nact > 1000, "the fixture must exercise contacts"
+    assert flips == 0, "active set / branch flips: %d" % flips
+    for k, v in worst.items():
+        assert v <= REL_TOL, (k, v)
+
+
+def test_contact64_free_running(torch_cuda):
+    """The same 64 worlds FREE RUNNING on the device for the whole fixture (120 steps, from first
+    touch-down into sliding contact): positions within 1e-6 of the real reference's own
+    trajectory, and active sets / branches identical at every step, for every world that has not
+    hit a branch tie (contact dynamics amplify the 1e-16 per-step differences; a world whose
+    friction-cone test is decided at that level flips -- those worlds are counted and bounded)."""
+    model, tr = _load_extra("human36_contact", "traj_human36_contact64.npz")
+    dt = float(tr["dt"])
+    W, T = tr["gpos"].shape[:2]
+    bw = _batch(model, W)
+    bw.set_state(tr["gpos_in"].T.copy(), tr["gvel_in"].T.copy(), np.zeros((model.nrows, W)))
+    first_flip = np.full(W, T)
+    err = np.zeros((T, W))
+    for s in range(T):
+        bw.step(dt, 1)
+        g, v, _ = bw.get_state()
+        a = bw.constraints("active").cpu().numpy()
+        br = bw.constraints("branch").cpu().numpy()
+        bad = (a != tr["active"][:, s]).any(1) | ((br*a) != tr["branch"][:, s]).any(1)
+        first_flip = np.where(bad & (first_flip == T), s, first_flip)
+        err[s] = np.abs(g.T - tr["gpos"][:, s]).max(1)
+    clean = first_flip == T
+    print("free-running contact: %d of %d worlds without any flip over %d steps; first flips at %s; "
+          "max |dq| of the clean worlds %.3g" % (clean.sum(), W, T, sorted(first_flip[~clean].tolist()),
+                                                  err[:, clean].max()))
+    assert clean.sum() >= int(0.9*W)
+    assert err[:, clean].max() < 1e-6
+    # before its first flip every world follows the reference
+    for w in np.nonzero(~clean)[0]:
+        assert err[:first_flip[w], w].max(initial=0.) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["human36_free", "snake_loop"])
+def test_free_running_1000_steps(torch_cuda, name):
+    """north_star: trajectories within 1e-6 after 1000 steps (configs 2 and 4), against
+    checkpoints of 1000 free-running steps of the real reference."""
+    model, tr = _load_extra(name, "free_%s.npz" % name)
+    W = tr["gpos"].shape[0]
+    bw = _batch(model, W)
+    bw.set_state(tr["gpos_in"].T.copy(), tr["gvel_in"].T.copy(),
+                 np.zeros((max(model.nrows, 1), W)))
+    done = 0
+    for i, k in enumerate(tr["kept_steps"]):
+        bw.step(float(tr["dt"]), int(k) + 1 - done)
+        done = int(k) + 1
+        g, v, f = bw.get_state()
+        assert np.abs(g.T - tr["gpos"][:, i]).max() < 1e-6, (name, int(k))
+        assert np.abs(v.T - tr["gvel"][:, i]).max() < 1e-6*max(1., np.abs(tr["gvel"][:, i]).max()), (name, int(k))
+    assert done == 1000
+    assert int(bw.status().max()) == 0
+
+
+@pytest.mark.parametrize("path", ["fused", "phases"])
+def test_per_world_pd_parameters(torch_cuda, path):
+    """every world its own kp, kd, gpos_des, gvel_des
+    (arb_batch_bind_controller_params) against the real reference run once per world with those
+    values on its ProportionalDerivativeController objects (controllers.py:113-159)."""
+    model, tr = _load_extra("zoo", "traj_zoo_pd.npz")
+    dt = float(tr["dt"])
+    W, T = tr["gpos"].shape[:2]
+    bw = _batch(model, W)
+    assert len(bw.pd_dofs()) == tr["pd_kp"].shape[0]
+    bw.set_controller_params(kp=tr["pd_kp"], kd=tr["pd_kd"], gpos_des=tr["pd_gpos_des"],
+                             gvel_des=tr["pd_gvel_des"])
+    gpos, gvel = tr["gpos_in"].T.copy(), tr["gvel_in"].T.copy()
+    cf = np.zeros((max(model.nrows, 1), W))
+    fs = list(tr["full_steps"])
+    worst = {}
+    for s in range(T):
+        bw.set_state(gpos, gvel, cf)
+        if path == "phases":
+            bw.update_dynamic()
+            bw.update_controllers(dt)
+            worst["gforce_ctrl"] = max(worst.get("gforce_ctrl", 0),
+                                       rel(bw.gforce().cpu().numpy(), tr["gforce_ctrl"][:, s]))
+            if s in fs:
+                for k in ("impedance", "admittance"):
+                    worst[k] = max(worst.get(k, 0), rel(bw.matrix(k).cpu().numpy(), tr[k][:, fs.index(s)]))
+            bw.update_constraints(dt)
+            bw.integrate(dt)
+        else:
+            bw.step(dt, 1)
+        g, v, _ = bw.get_state()
+        worst["gvel"] = max(worst.get("gvel", 0), rel(v.T, tr["gvel"][:, s]))
+        worst["gpos"] = max(worst.get("gpos", 0), rel(g.T, tr["gpos"][:, s]))
+        gpos, gvel = tr["gpos"][:, s].T.copy(), tr["gvel"][:, s].T.copy()
+        if model.nrows:
+            cf = tr["cforce"][:, s].T.copy()
+    for k, v in worst.items():
+        assert v <= REL_TOL, (k, v)
+    # and the worlds really differ: with the model's parameters the result is another one
+    bw.set_controller_params(kp=False, kd=False, gpos_des=False, gvel_des=False)
+    bw.set_state(tr["gpos_in"].T.copy(), tr["gvel_in"].T.copy(), np.zeros((max(model.nrows, 1), W)))
+    bw.step(dt, 1)
+    assert rel(bw.get_state()[1].T, tr["gvel"][:, 0]) > 1e-6
+
+
+def test_body_jacobians_on_device(torch_cuda):
+    """a3: Body.jacobian / djacobian / twist / nleffects read back from the DEVICE (arb_get_body)
+    against the oracle (pinned to the real reference by tests/test_oracle.py) on the 42-dof model."""
+    from oracle.arboris_oracle import OracleWorld
+    model, tr = load_golden("human36_free")
+    W = tr["gpos_in"].shape[0]
+    bw = _batch(model, W)
+    bw.set_state(tr["gpos_in"].T.copy(), tr["gvel_in"].T.copy())
+    bw.update_dynamic()
+    for w in range(W):
+        o = OracleWorld(model.to_dict())
+        o.gpos[:], o.gvel[:] = tr["gpos_in"][w], tr["gvel_in"][w]
+        o.update_dynamic()
+        for b in range(1, model.nj + 1):
+            assert rel(bw.body("jacobian", b, w, w + 1)[0].cpu().numpy(), o.jac[b]) < REL_TOL
+            assert rel(bw.body("djacobian", b, w, w + 1)[0].cpu().numpy(), o.djac[b]) < REL_TOL
+            assert rel(bw.body("twist", b, w, w + 1)[0].cpu().numpy(), o.twist[b]) < REL_TOL
+            assert rel(bw.body("pose", b, w, w + 1)[0].cpu().numpy(), o.pose[b]) < REL_TOL
+            nle = np.abs(o.body_nle[b]).max()
+            if nle > 0:
+                assert rel(bw.body("nleffects", b, w, w + 1)[0].cpu().numpy(), o.body_nle[b]) < REL_TOL
+
+
+def test_getters_refuse_stale_phase_scratch(torch_cuda):
+    """After a fused step the assembled matrices are not formed: the getters must say so instead
+    of returning what an earlier phase call left behind."""
+    from arboris_b200 import _capi
+    model, tr = load_golden("human36_free")
+    bw = _batch(model, 2)
+    bw.set_state(tr["gpos_in"][:2].T.copy(), tr["gvel_in"][:2].T.copy())
+    bw.update_dynamic()
+    bw.update_controllers(1e-3)
+    M0 = bw.matrix("mass").cpu().numpy()
+    bw.step(1e-3, 1)
+    for call in (lambda: bw.matrix("mass"), lambda: bw.gforce(), lambda: bw.body("jacobian", 1)):
+        with pytest.raises(_capi.ArbError):
+            call()
+    bw.body("pose", 1)                       # the fused step does leave poses and twists
+    bw.update_dynamic()
+    assert rel(bw.matrix("mass").cpu().numpy(), M0) > 0     # fresh, and the world has moved

@@ -224,3 +224,65 @@ def test_contact_aligned_blocks_are_detected():
         model, _ = load_golden(name)
         g, c = harness.HostBatch(model, 1).aligned()
         assert not g.any() and not c.any()
+
+
+def _extra(model_name, file_name):
+    import os
+    from conftest import GOLDEN
+    from arboris_b200.flatten import FlatModel
+    model = FlatModel.load(os.path.join(GOLDEN, "model_%s.npz" % model_name))
+    with np.load(os.path.join(GOLDEN, file_name)) as z:
+        return model, {k: z[k] for k in z.files}
+
+
+def test_fused_algorithm_vs_contact64():
+    """SURVEY.md 8(d) config 3 parity subset: 64 falling humanoids, 120 steps of the real reference;
+    the fused algorithm (host build of the device routines) from the reference's state at every step."""
+    model, tr = _extra("human36_contact", "traj_human36_contact64.npz")
+    dt = float(tr["dt"])
+    W, T = tr["gpos"].shape[:2]
+    hb = harness.HostBatch(model, W)
+    hb.set_coop(0)
+    gpos, gvel = tr["gpos_in"].T.copy(), tr["gvel_in"].T.copy()
+    cf = np.zeros((model.nrows, W))
+    flips, worst = 0, {}
+    for s in range(T):
+        hb.gpos[:], hb.gvel[:], hb.cforce[:] = gpos, gvel, cf
+        hb.fused_step(dt)
+        a = hb.iarr("factive", model.nc).T
+        br = hb.iarr("fbranch", model.nc).T
+        flips += int((a != tr["active"][:, s]).sum()) + int((br*a != tr["branch"][:, s]).sum())
+        for k, x in (("cforce", hb.cforce.T[:, :model.nrows]), ("gvel", hb.gvel.T), ("gpos", hb.gpos.T)):
+            worst[k] = max(worst.get(k, 0), rel(x, tr[k][:, s]))
+        gpos, gvel, cf = tr["gpos"][:, s].T.copy(), tr["gvel"][:, s].T.copy(), tr["cforce"][:, s].T.copy()
+    assert flips == 0
+    for k, v in worst.items():
+        assert v <= 1e-10, (k, v)
+
+
+@pytest.mark.parametrize("path", ["fused", "phases"])
+def test_per_world_pd_parameters_host(path):
+    """per-world kp, kd, gpos_des, gvel_des (arb_batch_bind_controller_params) against the real
+    reference stepped once per world with those values (tests/golden/traj_zoo_pd.npz)."""
+    model, tr = _extra("zoo", "traj_zoo_pd.npz")
+    dt = float(tr["dt"])
+    W, T = tr["gpos"].shape[:2]
+    hb = harness.HostBatch(model, W)
+    hb.set_coop(0)
+    hb.bind_params(tr["pd_kp"], tr["pd_kd"], tr["pd_gpos_des"], tr["pd_gvel_des"])
+    gpos, gvel = tr["gpos_in"].T.copy(), tr["gvel_in"].T.copy()
+    cf = np.zeros((max(model.nrows, 1), W))
+    worst = {}
+    for s in range(T):
+        hb.gpos[:], hb.gvel[:], hb.cforce[:] = gpos, gvel, cf
+        if path == "fused":
+            hb.fused_step(dt)
+        else:
+            hb.update_dynamic(); hb.update_controllers(dt); hb.update_constraints(dt); hb.integrate(dt)
+        worst["gvel"] = max(worst.get("gvel", 0), rel(hb.gvel.T, tr["gvel"][:, s]))
+        worst["gpos"] = max(worst.get("gpos", 0), rel(hb.gpos.T, tr["gpos"][:, s]))
+        gpos, gvel = tr["gpos"][:, s].T.copy(), tr["gvel"][:, s].T.copy()
+        if model.nrows:
+            cf = tr["cforce"][:, s].T.copy()
+    for k, v in worst.items():
+        assert v <= 1e-10, (k, v)

@@ -172,3 +172,62 @@ def test_oracle_free_running_simplearm():
     for s in range(1000):
         o.step(1e-3)
     assert np.abs(o.gpos - tr["gpos"][0, -1]).max() < 1e-12
+
+
+def _extra(model_name, file_name):
+    from arboris_b200.flatten import FlatModel
+    model = FlatModel.load(os.path.join(GOLDEN, "model_%s.npz" % model_name))
+    with np.load(os.path.join(GOLDEN, file_name)) as z:
+        return model, {k: z[k] for k in z.files}
+
+
+def test_oracle_vs_contact64_sample():
+    """The 64-world contact fixture (real reference, free running): the oracle from the reference's
+    state at every step, on a sample of the worlds (the whole fixture runs on the device)."""
+    model, tr = _extra("human36_contact", "traj_human36_contact64.npz")
+    dt = float(tr["dt"])
+    flips, worst = 0, 0.
+    for wi in (0, 17, 38, 63):
+        o = OracleWorld(model.to_dict())
+        gpos, gvel, cf = tr["gpos_in"][wi], tr["gvel_in"][wi], np.zeros(model.nrows)
+        for s in range(tr["gpos"].shape[1]):
+            o.gpos[:], o.gvel[:], o.cforce[:] = gpos, gvel, cf
+            o.step(dt)
+            a = np.array(o.active, dtype=np.int8)
+            flips += int((a != tr["active"][wi, s]).sum()) + int((np.array(o.branch)*a != tr["branch"][wi, s]).sum())
+            worst = max(worst, rel(o.gvel, tr["gvel"][wi, s]), rel(o.gpos, tr["gpos"][wi, s]),
+                        rel(o.cforce, tr["cforce"][wi, s]))
+            gpos, gvel, cf = tr["gpos"][wi, s], tr["gvel"][wi, s], tr["cforce"][wi, s]
+    assert flips == 0 and worst <= 1e-13, (flips, worst)
+
+
+@pytest.mark.parametrize("name,nworlds", [("human36_free", 1), ("snake_loop", 2)])
+def test_oracle_free_running_1000_steps(name, nworlds):
+    """1000 free-running steps of the oracle against checkpoints of the real reference."""
+    model, tr = _extra(name, "free_%s.npz" % name)
+    for wi in range(nworlds):
+        o = OracleWorld(model.to_dict())
+        o.gpos[:], o.gvel[:] = tr["gpos_in"][wi], tr["gvel_in"][wi]
+        done = 0
+        for i, k in enumerate(tr["kept_steps"]):
+            for _ in range(int(k) + 1 - done):
+                o.step(float(tr["dt"]))
+            done = int(k) + 1
+            assert np.abs(o.gpos - tr["gpos"][wi, i]).max() < 1e-9, (name, wi, int(k))
+
+
+def test_model_snapshot_follows_parameter_changes():
+    """the reference reads constraint / controller parameters live every step; the
+    single-world facade rebuilds its device model when one of them changes (and only then)."""
+    w = scenarios.zoo_world()
+    m0 = flatten(w)
+    for j in w.iterjoints():                    # moving the world is not a parameter change
+        if hasattr(j.gpos, "shape") and j.gpos.ndim == 1:
+            j.gpos[:] = j.gpos + 0.01
+    assert m0.same_parameters(flatten(w))
+    pd = [c for c in w._controllers if type(c).__name__ == "ProportionalDerivativeController"][0]
+    pd.gpos_des[0] += 0.5
+    assert not m0.same_parameters(flatten(w))
+    m1 = flatten(w)
+    w._constraints[0].disable()
+    assert not m1.same_parameters(flatten(w))
