@@ -67,6 +67,7 @@ static int model_to_device(arb_model* mo, int device) {
   rc |= upload(h.cgen1, &m.cgen1, own);   rc |= upload(h.cgen0, &m.cgen0, own);
   rc |= upload(h.gen_aligned, &m.gen_aligned, own); rc |= upload(h.gen_c0, &m.gen_c0, own);
   rc |= upload(h.caligned, &m.caligned, own);
+  rc |= upload(h.crunmask, &m.crunmask, own);
   m.ngen = h.ngen; m.ngrows = h.ngrows;
   rc |= upload(h.dofjoint, &m.dofjoint, own);   rc |= upload(h.jhaschild, &m.jhaschild, own);
   rc |= upload(h.jaccfirst, &m.jaccfirst, own); rc |= upload(h.jmark, &m.jmark, own);
@@ -77,6 +78,9 @@ static int model_to_device(arb_model* mo, int device) {
   rc |= upload(h.pd_qd, &m.pd_qd, own);         rc |= upload(h.pd_c, &m.pd_c, own);
   rc |= upload(h.pd_dqd, &m.pd_dqd, own);       rc |= upload(h.pd_index, &m.pd_index, own);
   m.npd = (int)h.pd_dofs.size();
+  rc |= upload(h.glev_off, &m.glev_off, own);   rc |= upload(h.glev_joint, &m.glev_joint, own);
+  rc |= upload(h.gslot, &m.gslot, own);         rc |= upload(h.gvslot, &m.gvslot, own);
+  m.gl = h.gl;
   m.has_pd = h.has_pd; m.gravity = h.gravity; m.nweight = h.nweight;
   if (rc) return -100;
   for (int i = 0; i < 3; ++i) m.up[i] = h.up[i];
@@ -172,6 +176,7 @@ extern "C" int arb_batch_set_option(arb_batch* b, const char* name, int value) {
   if (s == "force_phases") b->force_phases = value;
   else if (s == "gs_coop") b->gs_coop = value;
   else if (s == "sort_period") b->sort_period = value < 0 ? 0 : value;
+  else if (s == "prepare_group") b->prepare_group = value;
   else if (s == "time_stages") {
     b->time_stages = value;
     for (int i = 0; i < 4; ++i) b->stage_ms[i] = 0.;
@@ -563,6 +568,10 @@ extern "C" int arb_get_body(arb_batch* b, int which, int body, double* out, int6
   if (body < 0 || body > b->m.nj) { arb_set_error("body index out of range"); return -1; }
   if (which < ARB_BODY_POSE || which > ARB_BODY_NLE) { arb_set_error("unknown body quantity"); return -1; }
   const int64_t nw = w1 - w0;
+  if (from_fused && !b->poses_valid) {
+    arb_set_error("body poses / twists are not kept by arb_step with the group prepare stage: use arb_step_begin / arb_step_end");
+    return -2;
+  }
   if (from_fused) {
     k_get_body_fused<<<(unsigned)((nw + 127) / 128), 128, 0, b->stream>>>(b->d, which, body, out, w0, nw,
                                                                           arb_fused_world_slots(b));

@@ -6,6 +6,7 @@
 #include <string>
 
 #include "arb_fused.cuh"
+#include "arb_group.cuh"
 #include "arb_internal.h"
 
 // World sorting.  The Gauss-Seidel stage is executed warp by warp: a warp pays for a contact
@@ -109,6 +110,30 @@ __global__ void __launch_bounds__(FUSED_THREADS) k_fused_finish(DevModel m, DevB
   if (s < b.W) world_fused_finish(m, fused_tile_view(b, s), w, dt);
 }
 
+// prepare stage with a group of 16 lanes per world and the world's intermediates in shared memory
+// (arb_group.cuh); GROUP_WPC worlds per CTA, one record of m.gl.total doubles each
+#ifndef GROUP_WPC
+#define GROUP_WPC 2
+#endif
+__global__ void __launch_bounds__(GROUP_WPC * ARB_GL) k_fused_prepare_group(DevModel m, DevBatch b, double dt, int write_poses) {
+  extern __shared__ double gsm[];
+  const int gidx = threadIdx.x / ARB_GL;
+  const int64_t s = (int64_t)blockIdx.x * GROUP_WPC + gidx;
+  if (s >= b.W) return;
+  GroupCtx g;
+  g.sm = gsm + (size_t)gidx * m.gl.total;
+  g.lane = threadIdx.x % ARB_GL;
+  g.mask = 0xFFFFu << ((threadIdx.x & 31) & 16);
+  group_prepare(m, fused_tile_view(b, s), s, dt, g, write_poses != 0);
+}
+__global__ void __launch_bounds__(FUSED_THREADS) k_fused_finish_k(DevModel m, DevBatch b, double dt) {
+  FUSED_SLOT_WORLD();
+  if (s < b.W) world_fused_finish_k(m, fused_tile_view(b, s), w, dt);
+}
+static size_t group_smem_bytes(const arb_batch* b) { return sizeof(double) * (size_t)b->m.gl.total * GROUP_WPC; }
+// the group stage needs its per-world record to fit the SM's shared memory
+static bool group_supported(const arb_batch* b) { return group_smem_bytes(b) <= 227 * 1024; }
+
 // private by-slot state <- caller's state (GATHER) or the reverse; one thread per slot and
 // ELEMS_PER_BLOCK_Y elements, the by-slot side coalesced
 #define STATE_EPB 8
@@ -180,6 +205,8 @@ static int ensure_fused_scratch(arb_batch* b) {
     b->d.fkey = f->key[0];
   }
   CUDA_OKF(cudaFuncSetAttribute(k_fused_gs_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GS_COOP_SMEM));
+  if (group_supported(b))
+    CUDA_OKF(cudaFuncSetAttribute(k_fused_prepare_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem_bytes(b)));
   // the per-lane stages live on L1 (operands re-read every sweep / pass): no shared-memory carve-out
   CUDA_OKF(cudaFuncSetAttribute(k_fused_gs, cudaFuncAttributePreferredSharedMemoryCarveout, GS_L_SMEM ? 20 : 0));
   CUDA_OKF(cudaFuncSetAttribute(k_fused_prepare_lane, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
@@ -301,8 +328,13 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
       point_at_private();
       priv_valid = true;
     }
+    const bool grp = b->prepare_group && group_supported(b);
+    b->poses_valid = grp ? 0 : 1;      // (the group stage keeps poses on chip unless asked: arb_step_begin)
     if (ev[0]) cudaEventRecord(ev[0], b->stream);
-    k_fused_prepare_lane<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, d, dt);
+    if (grp)
+      k_fused_prepare_group<<<(unsigned)((W + GROUP_WPC - 1) / GROUP_WPC), GROUP_WPC * ARB_GL, group_smem_bytes(b), b->stream>>>(b->m, d, dt, 0);
+    else
+      k_fused_prepare_lane<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, d, dt);
     if (ev[0]) cudaEventRecord(ev[1], b->stream);
     if (b->m.nc > 0) {
       if (b->m.nc <= 64 && b->gs_coop)
@@ -312,7 +344,8 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
         k_fused_gs<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, d, dt);
     }
     if (ev[0]) cudaEventRecord(ev[2], b->stream);
-    k_fused_finish<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, d, dt);
+    if (grp) k_fused_finish_k<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, d, dt);
+    else k_fused_finish<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, d, dt);
     b->launches += (b->m.nc > 0) ? 3 : 2;
     ++f->steps;
     if (ev[0]) {   // diagnostic mode: per-stage device time of this step
@@ -347,12 +380,19 @@ int arb_fused_step_half(arb_batch* b, double dt, int half) {
     f->sorted = false;
     f->inv_valid = false;
   }
+  const bool grp = b->prepare_group && group_supported(b);
   if (half == 0) {
-    k_fused_prepare_lane<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    b->half_group = grp ? 1 : 0;       // the finish half must match the prepare half
+    b->poses_valid = 1;
+    if (grp)
+      k_fused_prepare_group<<<(unsigned)((W + GROUP_WPC - 1) / GROUP_WPC), GROUP_WPC * ARB_GL, group_smem_bytes(b), b->stream>>>(b->m, b->d, dt, 1);
+    else
+      k_fused_prepare_lane<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
     if (b->m.nc > 0) k_fused_gs<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
     b->launches += (b->m.nc > 0) ? 2 : 1;
   } else {
-    k_fused_finish<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    if (b->half_group) k_fused_finish_k<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    else k_fused_finish<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
     b->launches += 1;
     ++f->steps;
   }

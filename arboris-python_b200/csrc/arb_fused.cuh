@@ -30,7 +30,7 @@ ARB_D DevBatch fused_tile_view(const DevBatch& b, int64_t w) {
   t.fAcc += od; t.fP += od; t.faux += od; t.fpose += od; t.ff += od; t.fRe += od;
   t.aX += od; t.atw += od; t.ath += od; t.aS += od; t.aSh += od; t.aU += od; t.aLA += od;
   t.aLM += od; t.adinv += od; t.aIA += od; t.aIM += od; t.abeta += od; t.au += od; t.ax += od;
-  t.aV += od;
+  t.aV += od; t.fK += od;
   t.factive += oi; t.fbranch += oi; t.fzidx += oi;
   return t;
 }
@@ -796,6 +796,13 @@ ARB_D unsigned long long gs_sort_key(const DevModel& m, unsigned slid, unsigned 
   const int nb = m.nc < 32 ? m.nc : 32;
   return ((unsigned long long)slid << nb) | (unsigned long long)amask;
 }
+// the prepare stage's hand-over (v0 and the diagonal of Lambda) holds a NaN or an Inf
+ARB_D bool gs_world_nonfinite(const DevModel& m, const DevBatch& b) {
+  const int NG = m.ngrows;
+  double chk = 0.;
+  for (int g = 0; g < NG; ++g) chk += FT(b.fv0, g) + FT(b.fLam, g * NG + g);
+  return !isfinite(chk);
+}
 ARB_D unsigned long long world_fused_gs(const DevModel& m, const DevBatch& b, int64_t w, double dt,
                                         double* Lstore, int Lstride) {
   const int NG = m.ngrows;
@@ -805,6 +812,16 @@ ARB_D unsigned long long world_fused_gs(const DevModel& m, const DevBatch& b, in
   for (int c = 0; c < m.nc; ++c) any = any || FT(b.factive, c);
   for (int g = 0; g < NG; ++g) FT(b.fy, g) = 0.;
   if (!any) return 0ull;
+  // A world whose state has gone non-finite (the uncontrolled humanoid can blow up: the
+  // reference's own sliding solve diverges) gets NaN out of the reference too; here it must not
+  // cost more than a healthy world: with NaN operands every root finder and the QR fallback of
+  // the sliding solve run to their iteration caps in every visit (8 ms per world-step measured,
+  // a tail that kept one SM busy for 80 ms).  Flag it and leave: the finish stage propagates the
+  // NaN of q_free into the state exactly as the reference's arithmetic would.
+  if (gs_world_nonfinite(m, b)) {
+    b.status[w] |= ARB_STATUS_NONFINITE;
+    return 0ull;
+  }
   // constraint forces live in tiled scratch during the sweeps (ball-and-socket rows carry
   // the warm start, the others were reset by the prepare stage)
   for (int r = 0; r < m.nrows; ++r) FT(b.ff, r) = ST_LD(b.cforce, r);
@@ -829,10 +846,17 @@ ARB_D unsigned long long world_fused_gs(const DevModel& m, const DevBatch& b, in
     if (c == m.nc) { c = 0; ++sweep; }
     const bool last = v == nvis;
     const bool act = !last && (c < 32 ? ((amask >> c) & 1u) != 0u : FT(b.factive, c) != 0);
-    // Block switches are decided per WARP: every lane still in the loop follows the same
-    // sequence of cached blocks, so the flush/load code runs once per switch, not once per
-    // subset of lanes.  (A lane whose constraint c is inactive just skips the visit.)
-    if (!last && !arb_warp_any(act)) continue;
+    // Block switches are decided per WORLD and per RUN of constraints that share a cached block
+    // (crunmask): a lane takes part in the switch at the first constraint of a run iff one of ITS
+    // OWN constraints in the run is active -- so all the lanes of a warp that need the block switch
+    // together (the flush / load code runs once per run and warp), and the sequence of flushes,
+    // hence the rounding of the lazily updated rows, depends on the world's own active set alone:
+    // results are bit-identical whatever the batch size, the position in the batch or the sorting.
+    // (Decided per warp, a lane flushed early whenever a neighbour needed another block:
+    // u += L dy1 then u += L dy2 instead of u += L (dy1 + dy2) -- results depended on the warp's
+    // composition in the last bits.)
+    const bool needs = last || (c < 32 ? (amask & m.crunmask[c]) != 0u : act);
+    if (!needs) continue;
     const int type = last ? -1 : m.ctype[c];
     const int g1 = last ? -1 : m.cgen1[c], g0 = last ? -1 : m.cgen0[c];
     // the block this visit needs in the cache: a limited dof (1 row), the moving body of a
@@ -1069,6 +1093,10 @@ ARB_D unsigned long long world_fused_gs_coop(const DevModel& m, const DevBatch& 
       if (FT(b.factive, c)) amask |= 1ull << c;
     for (int g = 0; g < NG; ++g) FT(b.fy, g) = 0.;
   }
+  if (valid && amask != 0ull && gs_world_nonfinite(m, b)) {   // see world_fused_gs
+    b.status[w] |= ARB_STATUS_NONFINITE;
+    amask = 0ull;
+  }
   if (co.tid == 0) { *co.bm = 0ull; co.cnt[0] = 0; co.cnt[1] = 0; }
   coop_sync();
   coop_or(co.bm, amask);
@@ -1092,8 +1120,10 @@ ARB_D unsigned long long world_fused_gs_coop(const DevModel& m, const DevBatch& 
       const bool act = ((amask >> c) & 1ull) != 0ull;
       const int type = m.ctype[c];
       const int g1 = m.cgen1[c], g0 = m.cgen0[c];
+      // block switches per world and per run of constraints, as in world_fused_gs
+      const bool needs = c < 32 ? (amask & (unsigned long long)m.crunmask[c]) != 0ull : act;
       if (type == ARB_CONS_JOINT_LIMITS) {
-        if (live && k.g != g1) {
+        if (needs && k.g != g1) {
           gs_cache_flush(m, b, w, k);
           gs_cache_load<true>(m, b, w, k, g1, 1);
         }
@@ -1101,12 +1131,14 @@ ARB_D unsigned long long world_fused_gs_coop(const DevModel& m, const DevBatch& 
         continue;
       }
       if (g1 >= 0 && g0 >= 0) {
-        if (live) gs_cache_flush(m, b, w, k);
-        if (act) gs_visit_two_body(m, b, w, c, dt, &status);
+        if (act) {
+          gs_cache_flush(m, b, w, k);
+          gs_visit_two_body(m, b, w, c, dt, &status);
+        }
         continue;
       }
       const int gF = g1 < 0 ? g0 : g1;
-      if (live && k.g != gF) {
+      if (needs && k.g != gF) {
         gs_cache_flush(m, b, w, k);
         gs_cache_load<true>(m, b, w, k, gF, 6);
       }

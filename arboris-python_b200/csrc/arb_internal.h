@@ -32,7 +32,10 @@ struct arb_batch {
   double stage_ms[4] = {0., 0., 0., 0.};   // accumulated prepare / gs / finish milliseconds, [3] = steps timed
   FusedState* fused = nullptr;
   int sort_period = 2;             // fused path: re-sort the worlds by contact state every N steps (0: never)
+  int poses_valid = 1;             // the fused scratch holds the body poses / twists of the last fused step
+  int half_group = 0;              // arb_step_begin ran the group prepare stage: arb_step_end runs the K-matrix finish
   int half_open = 0;               // arb_step_begin ran the fused stages: arb_step_end must run the finish stage
+  int prepare_group = 0;           // 1: prepare stage with 16 lanes per world and on-chip scratch (arb_group.cuh) + K-matrix finish
   int last_fused = 0;              // 1: the constraint read-backs come from the fused scratch (last step was fused)
 };
 

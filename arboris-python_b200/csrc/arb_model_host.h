@@ -15,11 +15,14 @@ struct HostModel {
   std::vector<int> ctype, cint, crow, atype, aint;
   std::vector<int> dofbody, dofpos, gen_body, cgen1, cgen0;
   std::vector<int> gen_aligned, gen_c0, caligned;   // contact-aligned generator blocks (arb_fused.cuh)
+  std::vector<unsigned> crunmask;                   // runs of constraints on one cached Gauss-Seidel block
   int ngen = 0, ngrows = 0;
   // articulated-body tables
   std::vector<int> dofjoint, jhaschild, jaccfirst, jmark, jmarkfirst, jmarkchild, glimdof, pd_gpos;
   std::vector<int> pd_index, pd_dofs;   // per-world controller parameters: dof -> row (or -1), row -> dof
   int has_warm = 0;                     // some constraint force is state across steps (ball and socket)
+  std::vector<int> glev_off, glev_joint, gslot, gvslot;   // group prepare stage (arb_group.cuh)
+  GroupLayout gl;
   std::vector<int> jchild0, jsib;   // first child joint of body j+1 / next sibling joint (-1: none), ascending
   std::vector<double> pd_kp, pd_kd, pd_qd, pd_c, pd_dqd;
   int has_pd = 0, nweight = 0;
@@ -203,6 +206,25 @@ static inline int build_host_model(const arb_model_desc* d, HostModel& m, std::s
       m.cgen1[c] = m.ngrows++;
       m.glimdof.push_back(m.cint[ARB_CONS_NINT * c + 1]);
     }
+  // Runs of the Gauss-Seidel sweep: consecutive constraints that work on the same cached generator
+  // block (the moving body of a one-body constraint, or a limited dof).  A world switches to the
+  // block at the first constraint of the run iff one of ITS constraints in the run is active.
+  {
+    m.crunmask.assign(m.nc > 0 ? m.nc : 1, 0u);
+    auto block_of = [&](int c) {
+      if (m.ctype[c] == ARB_CONS_JOINT_LIMITS) return m.cgen1[c];
+      if (m.cgen1[c] >= 0 && m.cgen0[c] >= 0) return -1 - c;      // two-body constraint: no cached block, its own run
+      return m.cgen1[c] < 0 ? m.cgen0[c] : m.cgen1[c];
+    };
+    for (int c = 0; c < m.nc && c < 32; ) {
+      int e = c + 1;
+      while (e < m.nc && e < 32 && block_of(e) == block_of(c)) ++e;
+      unsigned mask = 0u;
+      for (int i = c; i < e; ++i) mask |= 1u << i;
+      for (int i = c; i < e; ++i) m.crunmask[i] = mask;
+      c = e;
+    }
+  }
   // articulated-body tables: tree shape, generator paths, controllers folded per dof
   m.dofjoint.assign(m.ndof, 0);
   for (int k = 0; k < m.ndof; ++k) m.dofjoint[k] = m.dofbody[k] - 1;
@@ -235,6 +257,56 @@ static inline int build_host_model(const arb_model_desc* d, HostModel& m, std::s
       m.jmarkchild[p - 1] = 1;
       if (!seenm[p]) { seenm[p] = 1; m.jmarkfirst[j] = 1; }
     }
+  }
+  // ---- group prepare stage: joints by depth, children slots, branch-point slots, shared-memory layout
+  {
+    std::vector<int> depth(nj, 0);
+    int nlev = 0;
+    for (int j = 0; j < nj; ++j) {
+      depth[j] = m.jparent[j] == 0 ? 0 : depth[m.jparent[j] - 1] + 1;
+      if (depth[j] + 1 > nlev) nlev = depth[j] + 1;
+    }
+    m.glev_off.assign(nlev + 1, 0);
+    m.glev_joint.clear();
+    for (int l = 0; l < nlev; ++l) {
+      m.glev_off[l] = (int)m.glev_joint.size();
+      for (int j = 0; j < nj; ++j)
+        if (depth[j] == l) m.glev_joint.push_back(j);
+    }
+    m.glev_off[nlev] = (int)m.glev_joint.size();
+    if (m.glev_joint.empty()) m.glev_joint.push_back(0);
+    m.gslot.assign(nj > 0 ? nj : 1, -1);
+    m.gvslot.assign(nj > 0 ? nj : 1, -1);
+    int nslot = 0, nvslot = 0;
+    for (int j = 0; j < nj; ++j) {
+      const int p = m.jparent[j];
+      if (p != 0 && p != j) m.gslot[j] = nslot++;           // (p == j: the parent body is the one of joint j-1, carried)
+      bool reread = false;                                    // a child other than joint j+1 reads (V, V^) of body j+1
+      for (int c = m.jchild0[j]; c >= 0; c = m.jsib[c])
+        if (c != j + 1) reread = true;
+      if (reread) m.gvslot[j] = nvslot++;
+    }
+    int maxpath = 1;
+    for (int g = 0; g < m.ngen; ++g)
+      if (m.kcols[m.gen_body[g]] > maxpath) maxpath = m.kcols[m.gen_body[g]];
+    for (size_t i = 0; i < m.glimdof.size(); ++i)
+      if (m.dofpos[m.glimdof[i]] + 1 > maxpath) maxpath = m.dofpos[m.glimdof[i]] + 1;
+    GroupLayout& L = m.gl;
+    const int n = m.ndof > 0 ? m.ndof : 1, njj = nj > 0 ? nj : 1;
+    int o = 0;
+    auto take = [&](int k) { int r = o; o += k; return r; };
+    L.X = take(12 * njj);
+    L.S = take(6 * n); L.Sh = take(6 * n); L.U = take(6 * n); L.LA = take(6 * n); L.LM = take(6 * n);
+    L.dinv = take(n); L.u0 = take(n);
+    const int kin = 24 * njj, slots = 78 * nslot;
+    L.kin = L.slot = take(kin > slots ? kin : slots);
+    L.ex = take(208);
+    const int ab = 42 * njj, solve = 16 * maxpath + 16 * 12 * nvslot;
+    L.ab = L.au = take(ab > solve ? ab : solve);
+    L.av = L.au + 16 * maxpath;
+    L.re = take(9 * (m.ngen > 0 ? m.ngen : 1));
+    L.total = o | 1;
+    L.nslot = nslot; L.nvslot = nvslot; L.maxpath = maxpath; L.nlev = nlev;
   }
   m.pd_kp.assign(m.ndof, 0.); m.pd_kd.assign(m.ndof, 0.); m.pd_qd.assign(m.ndof, 0.);
   m.pd_c.assign(m.ndof, 0.); m.pd_dqd.assign(m.ndof, 0.); m.pd_gpos.assign(m.ndof, -1);
@@ -292,10 +364,10 @@ static inline ScratchSizes scratch_sizes(const HostModel& m) {
 }
 struct FusedSizes {
   int64_t fq, fLam, fv0, fT1, fT0, fu, fy, fAcc, fP, faux, fpose, ff, fRe, factive, fbranch, fzidx;
-  int64_t aX, atw, ath, aS, aSh, aU, aLA, aLM, adinv, aIA, aIM, abeta, au, ax, aV;
+  int64_t aX, atw, ath, aS, aSh, aU, aLA, aLM, adinv, aIA, aIM, abeta, au, ax, aV, fK;
   int64_t total_doubles() const {
     return fq + fLam + fv0 + fT1 + fT0 + fu + fy + fAcc + fP + faux + fpose + ff + fRe +
-           aX + atw + ath + aS + aSh + aU + aLA + aLM + adinv + aIA + aIM + abeta + au + ax + aV;
+           aX + atw + ath + aS + aSh + aU + aLA + aLM + adinv + aIA + aIM + abeta + au + ax + aV + fK;
   }
   int64_t total_ints() const { return factive + fbranch + fzidx; }
 };
@@ -313,6 +385,7 @@ static inline FusedSizes fused_sizes(const HostModel& m) {
   s.aIA = s.aIM = nj * 36; s.abeta = nj * 6;
   const int64_t ng1 = m.ngen > 1 ? m.ngen : 1;   // six right-hand sides per generator body, all bodies in one pass
   s.au = 6 * ng1 * nn; s.ax = 6 * ng1 * nn; s.aV = nj * 72 * ng1;
+  s.fK = nn * NG;
   return s;
 }
 // Tiled layout: tile t of ARB_TILE worlds owns doubles [t*R*ARB_TILE, (t+1)*R*ARB_TILE), array X
@@ -330,6 +403,7 @@ static inline void carve_fused(const FusedSizes& s, double* dbl, int* ints, DevB
   b.aS = take(s.aS); b.aSh = take(s.aSh); b.aU = take(s.aU); b.aLA = take(s.aLA); b.aLM = take(s.aLM);
   b.adinv = take(s.adinv); b.aIA = take(s.aIA); b.aIM = take(s.aIM); b.abeta = take(s.abeta);
   b.au = take(s.au); b.ax = take(s.ax); b.aV = take(s.aV);
+  b.fK = take(s.fK);
   int* q = ints;
   auto takei = [&](int64_t k) { int* r = q; q += k * ARB_TILE; return r; };
   b.factive = takei(s.factive); b.fbranch = takei(s.fbranch); b.fzidx = takei(s.fzidx);

@@ -26,6 +26,19 @@ ARB_HDI int arb_cons_ndol(int t) {
 #define ARB_BODY_HASMASS 2   /* mass matrix not identically zero */
 #define ARB_BODY_HASVISC 4   /* viscosity matrix not identically zero */
 
+// Per-world shared-memory record of the group prepare stage (arb_group.cuh): offsets in doubles.
+struct GroupLayout {
+  int X, S, Sh, U, LA, LM, dinv, u0;   // what the solves read: X [nj][12]; S, Sh, U, LA, LM [n][6]; 1/d, u [n]
+  int kin;                             // kinematics area: pose [nj][12], T [nj][6], theta [nj][6]; dead after the
+  int slot;                            //   body terms and aliased with the children slots [nslot][78] of the factorisation
+  int ex;                              // exchange buffers of the factorisation (204) + flags (4)
+  int ab;                              // body terms [nj][42] (factorisation), aliased with
+  int au, av;                          //   reduced right-hand sides [16][maxpath] and branch-point (V, V^) [nvslot][16][12]
+  int re;                              // [ngen][9] frames of the contact-aligned generator bodies
+  int total;                           // doubles per world (odd, so that two worlds' records do not share banks)
+  int nslot, nvslot, maxpath, nlev;
+};
+
 // Read-only tables, device (or host, in the CPU unit-test build) pointers.
 struct DevModel {
   int ndof, ngpos, nj, nc, na, nrows;
@@ -59,6 +72,7 @@ struct DevModel {
   const int *gen_aligned;                      // [ngen] rows kept in the contact-aligned frame (arb_model_host.h)
   const int *gen_c0;                           // [ngen] first contact of an aligned generator (its plane normal)
   const int *caligned;                         // [nc] contact of an aligned generator: T is a translation
+  const unsigned *crunmask;                    // [nc] constraints (first 32) visited on the same cached Gauss-Seidel block, consecutively
   // ---- articulated-body tables (arb_artic.cuh) -----------------------------------------
   const int *dofjoint;                         // [ndof] joint of each dof
   const int *jhaschild;                        // [nj] body j+1 has child joints
@@ -76,6 +90,11 @@ struct DevModel {
   int npd;                                     // dofs driven by PD controllers (rows of the per-world parameters)
   double gravity;                              // sum of the WeightControllers' gravity
   int nweight;
+  // ---- group prepare stage (arb_group.cuh) ------------------------------------------------
+  GroupLayout gl;
+  const int *glev_off, *glev_joint;            // [nlev + 1], [nj] joints by depth (root-to-leaf scan)
+  const int *gslot;                            // [nj] children slot of joint j in the factorisation (or -1: carried / root)
+  const int *gvslot;                           // [nj] slot of body j+1's (V, V^) in the forward pass (or -1: never re-read)
 };
 
 // Per-batch memory: caller-owned state and the phase-API scratch are [elem][W]; the fused
@@ -134,4 +153,6 @@ struct DevBatch {
   double *au;        // [6 ngen][n]     reduced right-hand sides u_k, 6 per generator body
   double *ax;        // [6 ngen][n]     solutions
   double *aV;        // [nj][72 ngen]   (V, V^) of each body for 6 right-hand sides per generator body
+  // ---- group prepare stage: K = Z^-1 G^T, the generator solutions over ALL dofs -----------
+  double *fK;        // [n][NG]   (tiled like the rest of the fused scratch)
 };

@@ -320,9 +320,11 @@ def measure(a, scen, model, w0, w1, rank, world_size, local, full):
             ep.advance(PHASE)
             torch.cuda.synchronize()
     sampler.stop_flag = True
-    nonfinite = int((~torch.isfinite(bw.gvel)).any(0).sum())
+    bad = (~torch.isfinite(bw.gvel)).any(0)
+    nonfinite = int(bad.sum())
     out = {"W": W, "ms": ms, "launches": launches, "nonfinite": nonfinite, "warm": warm,
-           "clocks": sampler.summary(), "device": bw.device}
+           "clocks": sampler.summary(), "device": bw.device,
+           "nonfinite_ids": [int(x) + w0 for x in torch.nonzero(bad)[:8, 0].tolist()]}
 
     if full:
         # ---- active-set mix of the batch (for the mix-weighted flop count) and parity sample ------
@@ -497,6 +499,7 @@ def run_ours(a):
         "config": config_of(a, scen, total_worlds, W, world_size, a.scaling, model),
         "gpu_launches": int(head["launches"]),
         "nonfinite_worlds": int(head["nonfinite"]),
+        "nonfinite_world_ids": m["nonfinite_ids"],
         "roofline": {"bound": "fp64", "achieved": achieved/1e12, "peak": fp64_peak/1e12,
                      "unit": "TFLOP/s", "frac": achieved/fp64_peak if fp64_peak else None,
                      "frac_algorithmic": achieved/fp64_peak if fp64_peak else None,

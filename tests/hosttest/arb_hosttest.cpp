@@ -11,6 +11,7 @@
 #include "../../arboris-python_b200/csrc/arb_model_host.h"
 #include "../../arboris-python_b200/csrc/arb_world.cuh"
 #include "../../arboris-python_b200/csrc/arb_fused.cuh"
+#include "../../arboris-python_b200/csrc/arb_group.cuh"
 
 static DevModel view(const HostModel& h) {
   DevModel m;
@@ -25,7 +26,7 @@ static DevModel view(const HostModel& h) {
   for (int i = 0; i < 3; ++i) m.up[i] = h.up[i];
   m.dofbody = h.dofbody.data(); m.dofpos = h.dofpos.data(); m.ngen = h.ngen; m.ngrows = h.ngrows;
   m.gen_body = h.gen_body.data(); m.cgen1 = h.cgen1.data(); m.cgen0 = h.cgen0.data();
-  m.gen_aligned = h.gen_aligned.data(); m.gen_c0 = h.gen_c0.data(); m.caligned = h.caligned.data();
+  m.gen_aligned = h.gen_aligned.data(); m.gen_c0 = h.gen_c0.data(); m.caligned = h.caligned.data(); m.crunmask = h.crunmask.data();
   m.dofjoint = h.dofjoint.data(); m.jhaschild = h.jhaschild.data(); m.jaccfirst = h.jaccfirst.data();
   m.jmark = h.jmark.data(); m.jmarkfirst = h.jmarkfirst.data(); m.jmarkchild = h.jmarkchild.data();
   m.jchild0 = h.jchild0.data(); m.jsib = h.jsib.data();
@@ -33,6 +34,8 @@ static DevModel view(const HostModel& h) {
   m.pd_kd = h.pd_kd.data(); m.pd_qd = h.pd_qd.data(); m.pd_c = h.pd_c.data();
   m.pd_dqd = h.pd_dqd.data(); m.pd_index = h.pd_index.data(); m.npd = (int)h.pd_dofs.size();
   m.has_pd = h.has_pd; m.gravity = h.gravity; m.nweight = h.nweight;
+  m.gl = h.gl; m.glev_off = h.glev_off.data(); m.glev_joint = h.glev_joint.data();
+  m.gslot = h.gslot.data(); m.gvslot = h.gvslot.data();
   return m;
 }
 
@@ -95,6 +98,23 @@ void ht_integrate(void* p, double dt) {
   HostBatch* hb = (HostBatch*)p;
   for (int64_t w = 0; w < hb->b.W; ++w) world_integrate(hb->dm, hb->b, w, dt);
 }
+// the fused step with the group prepare stage (16 emulated lanes per world, arb_group.cuh), the
+// per-lane Gauss-Seidel and the K-matrix finish stage
+void ht_fused_step_group(void* p, double dt, int write_poses) {
+  HostBatch* hb = (HostBatch*)p;
+  std::vector<double> sm(hb->dm.gl.total, 0.);
+  for (int64_t w = 0; w < hb->b.W; ++w) {
+    const DevBatch t = fused_tile_view(hb->b, w);
+    for (size_t i = 0; i < sm.size(); ++i) sm[i] = 1e300;     // nothing may be read before it is written
+    GroupCtx g;
+    g.sm = sm.data(); g.lane = 0; g.mask = 0;
+    group_prepare(hb->dm, t, w, dt, g, write_poses != 0);
+    double Lst[36];
+    world_fused_gs(hb->dm, t, w, dt, Lst, 1);
+    world_fused_finish_k(hb->dm, t, w, dt);
+  }
+}
+int ht_group_doubles(void* p) { return ((HostBatch*)p)->dm.gl.total; }
 // the fused step in its scalar form: update_dynamic, prepare, gs, finish
 void ht_fused_step(void* p, double dt) {
   HostBatch* hb = (HostBatch*)p;

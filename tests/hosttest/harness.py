@@ -103,6 +103,15 @@ class HostBatch(object):
     def fused_step(self, dt):
         self.L.ht_fused_step(self.h, dt)
 
+    def fused_step_group(self, dt, write_poses=0):
+        """group prepare stage (lanes emulated) + per-lane Gauss-Seidel + K-matrix finish"""
+        self.L.ht_fused_step_group.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        self.L.ht_fused_step_group(self.h, dt, int(write_poses))
+
+    def group_doubles(self):
+        self.L.ht_group_doubles.argtypes = [C.c_void_p]
+        return int(self.L.ht_group_doubles(self.h))
+
     def arr(self, name, *shape):
         p = self.L.ht_array(self.h, name.encode())
         n = int(np.prod(shape))

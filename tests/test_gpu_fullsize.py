@@ -48,11 +48,13 @@ def env():
 def _status_ok(bw):
     """no world non-finite, singular or with a non-converged eigen-solve; ARB_STATUS_EIG_NOROOT
     (the reference's own silent clamp s = -1e10, constraints.py:827-830) is expected in a few
-    per cent of the falling humanoids: the numpy oracle takes that branch in the same worlds at
-    the same steps (worlds 5 and 70 of the first 96 seeds, steps 90 and 81)."""
+    per cent of the falling humanoids with round 1's gentler initial states and in ~12 % with
+    SURVEY.md's config-3 distribution (tilt up to 0.05 rad: feet start up to 1 cm inside the ground):
+    the numpy oracle takes that branch in the same worlds at the same steps (the 64-world fixture
+    of the real reference, tests/golden/traj_human36_contact64.npz, holds such visits)."""
     st = bw.status()
     assert int((st & ~4).max()) == 0
-    assert int((st != 0).sum()) <= max(1, bw.nworlds//20)
+    assert int((st != 0).sum()) <= max(1, bw.nworlds//5)
 
 
 def _oracle_steps(model, gpos, gvel, cforce, nsteps):
@@ -105,14 +107,15 @@ def test_config2_human36_free_4096(env):
     bw.update_dynamic()
     bw.update_controllers(DT)
     M, Z, Y = bw.matrix("mass"), bw.matrix("impedance"), bw.matrix("admittance")
+    Nh = bw.matrix("nleffects").cpu().numpy()
     assert (M - M.transpose(1, 2)).abs().max().item() < 1e-12*M.abs().max().item()
     eye = torch.eye(model.ndof, dtype=torch.float64, device=M.device)
     assert (torch.bmm(Z, Y) - eye).abs().max().item() < 1e-9
     assert torch.linalg.eigvalsh(M).min().item() > 0.          # M positive definite in every world
     # every world: the fused step against the assembled-matrix step
-    _fused_vs_phases(bw, torch, 1e-9)
+    _fused_vs_phases(bw, torch, 1e-10)
     # a sample against the oracle (M, N and the velocity after one step)
-    Mh, Nh = M.cpu().numpy(), bw.matrix("nleffects").cpu().numpy()
+    Mh = M.cpu().numpy()
     v1 = bw.gvel.cpu().numpy()
     from oracle.arboris_oracle import OracleWorld
     for w in (0, 1023, 2048, 4095):
@@ -137,7 +140,7 @@ def test_config3_human36_contact_16384(env):
     assert bool((v == v[:, :1]).all())
     g0 = bw.gpos[:, :3].cpu().numpy().copy()
     v0 = bw.gvel[:, :3].cpu().numpy().copy()
-    act = _fused_vs_phases(bw, torch, 1e-8)
+    act = _fused_vs_phases(bw, torch, 1e-10)
     nact = act.sum(1)
     assert int((nact >= 8).sum()) > 1000          # the contact path really ran
     assert bool((bw.constraints("active") == act).all())    # active sets: bit-exact on every world
@@ -170,7 +173,7 @@ def test_config4_snake_loops_16384(env):
     bw.update_dynamic(); bw.update_controllers(DT); bw.update_constraints(DT)
     sd = bw.constraints("sdist")
     assert bool(torch.isfinite(sd).all())
-    _fused_vs_phases(bw, torch, 1e-8)
+    _fused_vs_phases(bw, torch, 1e-10)
     assert int(bw.status().max()) == 0
 
 

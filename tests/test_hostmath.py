@@ -286,3 +286,37 @@ def test_per_world_pd_parameters_host(path):
             cf = tr["cforce"][:, s].T.copy()
     for k, v in worst.items():
         assert v <= 1e-10, (k, v)
+
+
+@pytest.mark.parametrize("name,tol", [("simplearm", 1e-12), ("human36_free", 1e-10), ("ball_socket", 1e-12),
+                                      ("simplearm_limits", 1e-12), ("snake_loop", 1e-10),
+                                      ("human36_contact", 1e-10), ("balls", 1e-10), ("zoo", 1e-10)])
+def test_group_prepare_vs_real_reference(name, tol):
+    """The prepare stage with 16 lanes per world and on-chip scratch (arb_group.cuh; the lanes of a
+    group are emulated one after the other between the barriers) + the K-matrix finish stage,
+    against the real reference's trajectories, from the reference's state at every step."""
+    model, tr = load_golden(name)
+    dt = float(tr["dt"])
+    W, T = tr["gpos"].shape[:2]
+    T = min(T, 150)
+    hb = harness.HostBatch(model, W)
+    gpos, gvel = tr["gpos_in"].T.copy(), tr["gvel_in"].T.copy()
+    cf = np.zeros((max(model.nrows, 1), W))
+    flips, worst = 0, {}
+    for s in range(T):
+        hb.gpos[:], hb.gvel[:], hb.cforce[:] = gpos, gvel, cf
+        hb.fused_step_group(dt)
+        if model.nc:
+            a = hb.iarr("factive", model.nc).T
+            br = hb.iarr("fbranch", model.nc).T
+            flips += int((a != tr["active"][:, s]).sum()) + int((br*a != tr["branch"][:, s]).sum())
+            worst["cforce"] = max(worst.get("cforce", 0), rel(hb.cforce.T[:, :model.nrows], tr["cforce"][:, s]))
+        worst["gvel"] = max(worst.get("gvel", 0), rel(hb.gvel.T, tr["gvel"][:, s]))
+        worst["gpos"] = max(worst.get("gpos", 0), rel(hb.gpos.T, tr["gpos"][:, s]))
+        gpos, gvel = tr["gpos"][:, s].T.copy(), tr["gvel"][:, s].T.copy()
+        if model.nrows:
+            cf = tr["cforce"][:, s].T.copy()
+    assert flips == 0
+    assert not hb.iarr("status").any()
+    for k, v in worst.items():
+        assert v <= tol, (k, v)
