@@ -68,6 +68,7 @@ static int model_to_device(arb_model* mo, int device) {
   rc |= upload(h.gen_aligned, &m.gen_aligned, own); rc |= upload(h.gen_c0, &m.gen_c0, own);
   rc |= upload(h.caligned, &m.caligned, own);
   rc |= upload(h.crunmask, &m.crunmask, own);
+  rc |= upload(h.doflim, &m.doflim, own);
   m.ngen = h.ngen; m.ngrows = h.ngrows;
   rc |= upload(h.dofjoint, &m.dofjoint, own);   rc |= upload(h.jhaschild, &m.jhaschild, own);
   rc |= upload(h.jaccfirst, &m.jaccfirst, own); rc |= upload(h.jmark, &m.jmark, own);

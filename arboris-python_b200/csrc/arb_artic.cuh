@@ -108,15 +108,38 @@ ARB_D void store_se3(double* arr, int j, const Se3& h) {
 // The passes below walk the joints in a fixed order and every operand of joint j was written
 // long before (by another pass): asking for the next joint's rows while working on this one
 // hides most of the DRAM / L2 latency that the 8 resident warps per SM cannot.
+#ifndef ARB_PREFETCH_MODE
+#define ARB_PREFETCH_MODE 1     /* 0: none, 1: into L1, 2: into L2 only (A/B builds) */
+#endif
 ARB_D void arb_prefetch(const double* p) {
-#ifdef __CUDA_ARCH__
+#if defined(__CUDA_ARCH__) && ARB_PREFETCH_MODE == 1
   asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#elif defined(__CUDA_ARCH__) && ARB_PREFETCH_MODE == 2
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 #endif
 }
 template <int N>
 ARB_D void arb_prefetch_rows(const double* p) {
 #pragma unroll
   for (int i = 0; i < N; ++i) arb_prefetch(p + i * ARB_TILE);
+}
+// Rows of the scratch that were just read for the LAST time before they are written again (the
+// children's slots of the factorisation, the (V, V^) a body hands to its children): tell the L2 to
+// drop them instead of writing them back to HBM (discard.global.L2, 128 bytes per instruction:
+// lanes 0 and 16 cover the 256-byte row of the warp's 32 worlds).  The barrier orders the other
+// lanes' loads of the row before the discard.  Contents are undefined afterwards, until rewritten.
+#ifndef ARB_DISCARD
+#define ARB_DISCARD 1
+#endif
+template <int N>
+ARB_D void arb_discard_rows(const double* p) {
+#if defined(__CUDA_ARCH__) && ARB_DISCARD
+  __syncwarp(__activemask());
+  if ((threadIdx.x & 15) == 0) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) asm volatile("discard.global.L2 [%0], 128;" ::"l"(p + i * ARB_TILE) : "memory");
+  }
+#endif
 }
 // per-dof rows of joint j in the four arrays a0..a3 (6 rows per dof each)
 ARB_D void artic_prefetch_dofs(const DevModel& m, int j, const double* a0, const double* a1,
@@ -355,6 +378,9 @@ ARB_D bool artic_factor(const DevModel& m, const DevBatch& b, int64_t w, double 
       for (int i = 0; i < 36; ++i) { IA[i] += pa[i * ARB_TILE]; IM[i] += pm[i * ARB_TILE]; }
 #pragma unroll
       for (int i = 0; i < 6; ++i) beta[i] += pb[i * ARB_TILE];
+      arb_discard_rows<36>(pa);      // dead until joint c writes its slot again in the next step
+      arb_discard_rows<36>(pm);
+      arb_discard_rows<6>(pb);
     }
     for (int c = nd - 1; c >= 0; --c) {
       const int k = dof + c;
@@ -457,7 +483,9 @@ ARB_D void artic_down(const Se3& X, double* V, double* Vh) {
 // LA, LM, s, s^ are read once for all of them): unit generalized forces on the dofs ek[e], whose
 // reduced right-hand sides artic_backward_generators left in au[1 + e]; solutions to ax[e],
 // (V, Vh) to aV[j][12 (1 + e) ..].
-template <bool MARKED_U, int NE>
+// PF: prefetch the next joint's rows (pays in the prepare stage; the finish stage, which only runs
+// this one pass over rows nothing else touched for a whole Gauss-Seidel, is 12 % faster without).
+template <bool MARKED_U, int NE, bool PF = true>
 ARB_D void artic_forward_full(const DevModel& m, const DevBatch& b, int64_t w, const double* u, double* x,
                               bool ext = false, const int* ek = nullptr) {
   const int n = m.ndof;
@@ -471,7 +499,7 @@ ARB_D void artic_forward_full(const DevModel& m, const DevBatch& b, int64_t w, c
   }
   int prev = -2;
   for (int j = 0; j < m.nj; ++j) {
-    if (j + 1 < m.nj) {
+    if (PF && j + 1 < m.nj) {
       arb_prefetch_rows<12>(b.aX + (j + 1) * (12 * ARB_TILE));
       artic_prefetch_dofs(m, j + 1, b.aLA, b.aLM, b.aS, b.aSh);
     }
@@ -743,6 +771,17 @@ ARB_D void artic_forward_generators_all(const DevModel& m, const DevBatch& b, in
           }
           artic_down(X, V[r], Vh[r]);
         }
+        // last reader of the parent's (V, V^): the generator rows read V (first 6 of 12) of generator
+        // bodies later, everything else is dead
+        if (m.jmarkfirst[j]) {
+          const bool pgen = artic_is_gen_body(m, par - 1);
+#pragma unroll
+          for (int r = 0; r < 6; ++r) {
+            const double* pv = b.aV + ((par - 1) * VS + (rb + r) * 12) * ARB_TILE;
+            if (!pgen) arb_discard_rows<6>(pv);
+            arb_discard_rows<6>(pv + 6 * ARB_TILE);
+          }
+        }
       }
       for (int c = 0; c < nd; ++c) {
         const int k = dof + c;
@@ -761,17 +800,19 @@ ARB_D void artic_forward_generators_all(const DevModel& m, const DevBatch& b, in
 #pragma unroll
             for (int i = 0; i < 6; ++i) t -= LA[i] * V[r][i] + LM[i] * Vh[r][i];
           }
-          FT(b.ax, (rb + r) * n + k) = t;
+          if (m.doflim[k]) FT(b.ax, (rb + r) * n + k) = t;     // (only joint-limit rows read a solution back)
 #pragma unroll
           for (int i = 0; i < 6; ++i) { V[r][i] += s[i] * t; Vh[r][i] += sh[i] * t; }
         }
       }
+      // (V, V^) for the children; a leaf of the marked tree only hands V to the generator rows
+      const bool vh_read = m.jmarkchild[j] != 0;
 #pragma unroll
       for (int r = 0; r < 6; ++r)
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
           FT(b.aV, j * VS + (rb + r) * 12 + i) = V[r][i];
-          FT(b.aV, j * VS + (rb + r) * 12 + 6 + i) = Vh[r][i];
+          if (vh_read) FT(b.aV, j * VS + (rb + r) * 12 + 6 + i) = Vh[r][i];
         }
     }
   }

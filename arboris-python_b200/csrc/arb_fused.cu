@@ -68,12 +68,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, PREP_MINBLOCKS) k_fused_prepare
   if (s >= b.W) return;
   world_fused_prepare(m, fused_tile_view(b, s), w, dt);
 }
-__global__ void __launch_bounds__(FUSED_THREADS, GS_MINBLOCKS) k_fused_gs(DevModel m, DevBatch b, double dt) {
+// threads per CTA of the Gauss-Seidel kernel.  At 255 registers per thread this also sets the
+// number of resident warps per SM (64: 8 warps, 96: 6, 160: 5, 224: 7): the stage re-reads the
+// same ~3.5 KB of operands per world in every sweep, and whether the worlds in flight fit the L2
+// between two sweeps matters more than thread-level parallelism (profiles/README.md, round 2).
+#ifndef GS_THREADS
+#define GS_THREADS FUSED_THREADS
+#endif
+__global__ void __launch_bounds__(GS_THREADS, GS_MINBLOCKS) k_fused_gs(DevModel m, DevBatch b, double dt) {
   FUSED_SLOT_WORLD();
   if (s >= b.W) return;
 #if GS_L_SMEM
-  __shared__ double sL[36 * FUSED_THREADS];
-  const unsigned long long key = world_fused_gs(m, fused_tile_view(b, s), w, dt, sL + threadIdx.x, FUSED_THREADS);
+  __shared__ double sL[36 * GS_THREADS];
+  const unsigned long long key = world_fused_gs(m, fused_tile_view(b, s), w, dt, sL + threadIdx.x, GS_THREADS);
 #else
   double Lr[36];
   const unsigned long long key = world_fused_gs(m, fused_tile_view(b, s), w, dt, Lr, 1);
@@ -341,7 +348,7 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
         k_fused_gs_coop<<<(unsigned)((W + GS_COOP_THREADS - 1) / GS_COOP_THREADS), GS_COOP_THREADS,
                           GS_COOP_SMEM, b->stream>>>(b->m, d, dt);
       else
-        k_fused_gs<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, d, dt);
+        k_fused_gs<<<(unsigned)((W + GS_THREADS - 1) / GS_THREADS), GS_THREADS, 0, b->stream>>>(b->m, d, dt);
     }
     if (ev[0]) cudaEventRecord(ev[2], b->stream);
     if (grp) k_fused_finish_k<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, d, dt);
@@ -388,7 +395,7 @@ int arb_fused_step_half(arb_batch* b, double dt, int half) {
       k_fused_prepare_group<<<(unsigned)((W + GROUP_WPC - 1) / GROUP_WPC), GROUP_WPC * ARB_GL, group_smem_bytes(b), b->stream>>>(b->m, b->d, dt, 1);
     else
       k_fused_prepare_lane<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
-    if (b->m.nc > 0) k_fused_gs<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    if (b->m.nc > 0) k_fused_gs<<<(unsigned)((W + GS_THREADS - 1) / GS_THREADS), GS_THREADS, 0, b->stream>>>(b->m, b->d, dt);
     b->launches += (b->m.nc > 0) ? 2 : 1;
   } else {
     if (b->half_group) k_fused_finish_k<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);

@@ -1172,7 +1172,7 @@ ARB_D void world_fused_finish(const DevModel& m, const DevBatch& b, int64_t w, d
   // q'+ = q_free + Z^-1 G^T y
   if (any) {
     artic_backward_wrenches(m, b, w, b.fy);
-    artic_forward_full<true, 0>(m, b, w, b.au, b.ax);
+    artic_forward_full<true, 0, false>(m, b, w, b.au, b.ax);
   }
   bool finite = true;
   for (int j = 0; j < m.nj; ++j) {

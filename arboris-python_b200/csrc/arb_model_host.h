@@ -15,6 +15,7 @@ struct HostModel {
   std::vector<int> ctype, cint, crow, atype, aint;
   std::vector<int> dofbody, dofpos, gen_body, cgen1, cgen0;
   std::vector<int> gen_aligned, gen_c0, caligned;   // contact-aligned generator blocks (arb_fused.cuh)
+  std::vector<int> doflim;
   std::vector<unsigned> crunmask;                   // runs of constraints on one cached Gauss-Seidel block
   int ngen = 0, ngrows = 0;
   // articulated-body tables
@@ -206,6 +207,8 @@ static inline int build_host_model(const arb_model_desc* d, HostModel& m, std::s
       m.cgen1[c] = m.ngrows++;
       m.glimdof.push_back(m.cint[ARB_CONS_NINT * c + 1]);
     }
+  m.doflim.assign(m.ndof > 0 ? m.ndof : 1, 0);
+  for (size_t i = 0; i < m.glimdof.size(); ++i) m.doflim[m.glimdof[i]] = 1;
   // Runs of the Gauss-Seidel sweep: consecutive constraints that work on the same cached generator
   // block (the moving body of a one-body constraint, or a limited dof).  A world switches to the
   // block at the first constraint of the run iff one of ITS constraints in the run is active.

@@ -82,6 +82,7 @@ struct DevModel {
   const int *jmarkchild;                       // [nj] body j+1 has marked child joints
   const int *jchild0, *jsib;                   // [nj] first child joint of body j+1 / next sibling joint (-1: none)
   const int *glimdof;                          // [ngrows - 6 ngen] dof of each joint-limit generator row
+  const int *doflim;                           // [ndof] the dof carries a joint-limit generator row (its solutions are read back)
   // diagonal PD controllers folded per dof: tau = kp (qd - q) + c, Z[k][k] += dt kp + kd
   int has_pd;
   const double *pd_kp, *pd_kd, *pd_qd, *pd_c, *pd_dqd;  // [ndof]

@@ -26,7 +26,7 @@ static DevModel view(const HostModel& h) {
   for (int i = 0; i < 3; ++i) m.up[i] = h.up[i];
   m.dofbody = h.dofbody.data(); m.dofpos = h.dofpos.data(); m.ngen = h.ngen; m.ngrows = h.ngrows;
   m.gen_body = h.gen_body.data(); m.cgen1 = h.cgen1.data(); m.cgen0 = h.cgen0.data();
-  m.gen_aligned = h.gen_aligned.data(); m.gen_c0 = h.gen_c0.data(); m.caligned = h.caligned.data(); m.crunmask = h.crunmask.data();
+  m.gen_aligned = h.gen_aligned.data(); m.gen_c0 = h.gen_c0.data(); m.caligned = h.caligned.data(); m.crunmask = h.crunmask.data(); m.doflim = h.doflim.data();
   m.dofjoint = h.dofjoint.data(); m.jhaschild = h.jhaschild.data(); m.jaccfirst = h.jaccfirst.data();
   m.jmark = h.jmark.data(); m.jmarkfirst = h.jmarkfirst.data(); m.jmarkchild = h.jmarkchild.data();
   m.jchild0 = h.jchild0.data(); m.jsib = h.jsib.data();
