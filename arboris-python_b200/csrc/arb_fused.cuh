@@ -309,7 +309,8 @@ ARB_D void gs_cache_flush(const DevModel& m, const DevBatch& b, int64_t w, GsCac
   for (int p = 0; p < 6; ++p) any = any || (p < k.n && k.dy[p] != 0.);
   double* pu = b.fu + k.g * ARB_TILE;
   if (any) {
-    double* py = b.fy + k.g * ARB_TILE;
+    // (the accumulated wrench y is not maintained during the sweeps: gs_final_wrench forms it from
+    // the final forces, as the reference forms gforce += J^T f, core.py:936-937)
     const double* pl = b.fLam + k.g * ARB_TILE;        // Lambda[r, g + p] = pl[(r NG + p) TILE]
     const int rowstride = NG * ARB_TILE;
     // Rows outside the block, four at a time: the loads of four rows are in flight together
@@ -320,13 +321,14 @@ ARB_D void gs_cache_flush(const DevModel& m, const DevBatch& b, int64_t w, GsCac
     if (k.n == 6) {
 #pragma unroll 1
       for (int i0 = 0; i0 < nout; i0 += 4) {
-        double acc[4];
+        double acc[4], uu[4];
         int rr[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int ii = i0 + i < nout ? i0 + i : nout - 1;
           rr[i] = ii < k.g ? ii : ii + 6;
           const double* q = pl + rr[i] * rowstride;
+          uu[i] = b.fu[rr[i] * ARB_TILE];       // (in flight with the Lambda rows: one round trip, not two)
           double a = 0.;
 #pragma unroll
           for (int p = 0; p < 6; ++p) a += q[p * ARB_TILE] * k.dy[p];
@@ -334,10 +336,8 @@ ARB_D void gs_cache_flush(const DevModel& m, const DevBatch& b, int64_t w, GsCac
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (i0 + i < nout) b.fu[rr[i] * ARB_TILE] += acc[i];
+          if (i0 + i < nout) b.fu[rr[i] * ARB_TILE] = uu[i] + acc[i];
       }
-#pragma unroll
-      for (int p = 0; p < 6; ++p) py[p * ARB_TILE] += k.dy[p];
     } else {
 #pragma unroll 1
       for (int i0 = 0; i0 < nout; i0 += 4) {
@@ -354,7 +354,6 @@ ARB_D void gs_cache_flush(const DevModel& m, const DevBatch& b, int64_t w, GsCac
         for (int i = 0; i < 4; ++i)
           if (i0 + i < nout) b.fu[rr[i] * ARB_TILE] = uu[i] + lam[i] * k.dy[0];
       }
-      py[0] += k.dy[0];
     }
   }
   if (k.n == 6) {
@@ -446,7 +445,6 @@ ARB_NOINLINE void gs_visit_two_body(const DevModel& m, const DevBatch& b, int64_
       double acc = 0.;
       for (int i = 0; i < nd; ++i) acc += FT(Ts, c * 24 + i * 6 + p) * df[i];
       wv[p] = sign * acc;
-      FT(b.fy, gs + p) += wv[p];
     }
     for (int g = 0; g < NG; ++g) {
       double acc = 0.;
@@ -787,6 +785,44 @@ ARB_D void gs_visit_limit(const DevModel& m, const DevBatch& b, int c, double dt
   }
 }
 
+// y = sum_c T_c^T f_c from the FINAL constraint forces (generator-space image of the reference's
+// gforce += J^T f, core.py:936-937): what the finish stage solves with.
+ARB_D void gs_final_wrench(const DevModel& m, const DevBatch& b) {
+  const int NG = m.ngrows;
+  for (int g = 0; g < NG; ++g) FT(b.fy, g) = 0.;
+  for (int c = 0; c < m.nc; ++c) {
+    if (!FT(b.factive, c)) continue;
+    const int type = m.ctype[c];
+    const int r0 = m.crow[c];
+    if (type == ARB_CONS_JOINT_LIMITS) {
+      FT(b.fy, m.cgen1[c]) += FT(b.ff, r0);
+      continue;
+    }
+    const int nd = arb_cons_ndol(type);
+    double f[4] = {0., 0., 0., 0.};
+    for (int i = 0; i < nd; ++i) f[i] = FT(b.ff, r0 + i);
+    for (int s = 0; s < 2; ++s) {
+      const int gs = s ? m.cgen0[c] : m.cgen1[c];
+      if (gs < 0) continue;
+      const double* Ts = (s ? b.fT0 : b.fT1) + c * (24 * ARB_TILE);
+      double wv[6];
+      if (m.caligned[c]) {
+        gs_aligned_wrench(Ts, f, wv);
+      } else {
+        const double sign = s ? -1. : 1.;
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+          double acc = 0.;
+          for (int i = 0; i < nd; ++i) acc += Ts[(i * 6 + p) * ARB_TILE] * f[i];
+          wv[p] = sign * acc;
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < 6; ++p) FT(b.fy, gs + p) += wv[p];
+    }
+  }
+}
+
 #ifdef ARB_HOSTTEST_COUNTERS
 static unsigned* arb_dbg_slidemask = nullptr;   // host unit tests only: [W][sweeps] mask of contacts that slid
 #endif
@@ -885,6 +921,7 @@ ARB_D unsigned long long world_fused_gs(const DevModel& m, const DevBatch& b, in
 #endif
     }
   }
+  gs_final_wrench(m, b);
   for (int r = 0; r < m.nrows; ++r) ST(b.cforce, r) = FT(b.ff, r);
   if (status) b.status[w] |= status;
   return gs_sort_key(m, slid, amask);
@@ -1159,6 +1196,7 @@ ARB_D unsigned long long world_fused_gs_coop(const DevModel& m, const DevBatch& 
   }
   if (live) {
     gs_cache_flush(m, b, w, k);
+    gs_final_wrench(m, b);
     for (int r = 0; r < m.nrows; ++r) ST(b.cforce, r) = FT(b.ff, r);
     if (status) b.status[w] |= status;
   }
