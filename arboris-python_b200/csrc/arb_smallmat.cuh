@@ -447,11 +447,17 @@ ARB_NOINLINE int poly6_roots_slow(const double* p, double T, double* roots) { re
 
 #ifdef ARB_HOSTTEST_COUNTERS
 static long arb_fastroot_hits = 0;   // host unit tests only: how often the fast path certified its root
+static long arb_fastroot_fail[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // ... and why it did not (by exit), [7] = Laguerre iterations
+#endif
+#ifdef ARB_HOSTTEST_COUNTERS
+#define ARB_FAIL(i) (++arb_fastroot_fail[i], 0)
+#else
+#define ARB_FAIL(i) 0
 #endif
 ARB_HD int poly6_largest_root_fast(const double* p, double* root) {
   const double mean = -p[5] * (1. / 6.);
   const double var = (p[5] * p[5] - 2. * p[4]) * (1. / 6.) - mean * mean;
-  if (!(var >= 0.)) return 0;
+  if (!(var >= 0.)) return ARB_FAIL(0);
   double x = mean + 2.2360679774997898 * sqrt(var);
   x += 1e-12 * fabs(x) + 1e-300;
   bool conv = false;
@@ -466,18 +472,21 @@ ARB_HD int poly6_largest_root_fast(const double* p, double* root) {
       f = f * x + p[k];
       e = e * ax + fabs(f);
     }
+#ifdef ARB_HOSTTEST_COUNTERS
+    ++arb_fastroot_fail[7];
+#endif
     if (fabs(f) <= 2.5e-16 * e) { conv = true; break; }
-    if (!(f > 0.)) return 0;                    // fell to the left of a root: not real-rooted
+    if (!(f > 0.)) return ARB_FAIL(1);                    // fell to the left of a root: not real-rooted
     // Laguerre step n / (G + sqrt((n-1)(n H - G^2))), G = p'/p, H = G^2 - p''/p, n = 6, with the
     // common factor 1/p taken out (d2 holds p''/2): one square root and one division
     const double disc = 5. * (5. * d1 * d1 - 12. * f * d2);
-    if (!(disc >= 0.) || !(d1 > 0.)) return 0;
+    if (!(disc >= 0.) || !(d1 > 0.)) return ARB_FAIL(2);
     const double a = 6. * f / (d1 + sqrt(disc));
     const double xn = x - a;
     if (!(a > 2.5e-16 * fabs(x))) { conv = true; break; }
     x = xn;
   }
-  if (!conv) return 0;
+  if (!conv) return ARB_FAIL(3);
   // Taylor coefficients of p at x (repeated synthetic division), b[1..5] must be > 0
   double b[7];
 #pragma unroll
@@ -490,7 +499,7 @@ ARB_HD int poly6_largest_root_fast(const double* p, double* root) {
   bool pos = true;
 #pragma unroll
   for (int k = 1; k < 6; ++k) pos = pos && (b[k] > 0.);
-  if (!pos) return 0;
+  if (!pos) return ARB_FAIL(4);
   *root = x;
 #ifdef ARB_HOSTTEST_COUNTERS
   ++arb_fastroot_hits;

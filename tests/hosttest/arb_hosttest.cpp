@@ -185,6 +185,7 @@ int ht_sliding_root(const double* A, const double* alpha, double mu, double* s, 
   return ok ? 1 : 0;
 }
 long ht_fastroot_hits() { return arb_fastroot_hits; }
+long ht_fastroot_fail(int i) { return arb_fastroot_fail[i]; }
 void ht_set_slidemask(unsigned* p) { arb_dbg_slidemask = p; }
 // number of generator bodies; flags[g] = 1 for contact-aligned ones, caligned[c] per constraint
 int ht_aligned(void* p, int* flags, int* caligned) {
