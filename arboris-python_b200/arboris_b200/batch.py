@@ -368,7 +368,7 @@ class HostPipeline(object):
     ``gpos``, ``gvel``, ``cforce`` are C-contiguous (elem, W) numpy arrays over PINNED memory
     (e.g. ``torch.empty(...).pin_memory().numpy()``), updated in place."""
 
-    def __init__(self, world_or_model, nworlds, chunks=(1, 1, 2, 2, 2, 1, 1), device=None, mode="serial",
+    def __init__(self, world_or_model, nworlds, chunks="auto", device=None, mode="serial",
                  compute_streams=3):
         """``chunks``: number of equal column blocks or their relative sizes (``shard.block_ranges``).
         ``mode="serial"`` (default): the kernels of ALL blocks on ``compute_streams`` streams, block
@@ -382,6 +382,9 @@ class HostPipeline(object):
         assert mode in ("streams", "serial")
         self.mode = mode
         self.nworlds = int(nworlds)
+        if chunks == "auto":
+            chunks = self.auto_chunks(self.nworlds)
+        self.chunks = chunks
         self.ranges = block_ranges(self.nworlds, chunks)
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         serial = mode == "serial"
@@ -397,6 +400,18 @@ class HostPipeline(object):
                                 for i, (w0, w1) in enumerate(self.ranges[1:])]
         self._ev = [(torch.cuda.Event(), torch.cuda.Event()) for _ in self.parts] if serial else None
         torch.cuda.synchronize(dev)      # construction ran on the default stream
+
+    @staticmethod
+    def auto_chunks(nworlds):
+        """Column blocks by batch size: a block should still fill the GPU (148 SMs x 256 resident
+        worlds = 37888), so small batches are not split -- 32768 worlds per GPU (262144 over 8 GPUs)
+        go through as ONE block (copy in, step, copy out: 3.7 ms instead of 8.1 ms in seven slivers),
+        mid-sized ones as 1:2:1, large ones as the measured best 1:1:2:2:2:1:1."""
+        if nworlds < 49152:
+            return 1
+        if nworlds < 163840:
+            return (1, 2, 1)
+        return (1, 1, 2, 2, 2, 1, 1)
 
     def set_option(self, name, value):
         for p in self.parts:

@@ -91,9 +91,10 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity-sample", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.)
-    ap.add_argument("--e2e-chunks", type=lambda t: [int(x) for x in t.split(",")] if "," in t else int(t), default=[1, 1, 2, 2, 2, 1, 1],
-                    help="column blocks of the end-to-end pass: a number of equal blocks or their relative "
-                         "sizes (a,b,c,...); 1 = one synchronous arb_step_host call per step")
+    ap.add_argument("--e2e-chunks", type=lambda t: t if t == "auto" else ([int(x) for x in t.split(",")] if "," in t else int(t)),
+                    default="auto",
+                    help="column blocks of the end-to-end pass: 'auto' (by batch size, HostPipeline.auto_chunks), a "
+                         "number of equal blocks or their relative sizes (a,b,c,...)")
     ap.add_argument("--e2e-mode", default="serial", choices=["serial", "streams"],
                     help="HostPipeline mode: 'serial' = the kernels of all blocks on --e2e-compute-streams "
                          "streams, block after block, copies on two more streams; 'streams' = one stream per block")
@@ -358,11 +359,14 @@ def measure(a, scen, model, w0, w1, rank, world_size, local, full):
         hep.state, hep.init = (hg, hv, hf), (torch.as_tensor(gp), torch.as_tensor(gv), None)
 
         pipe = None
-        if isinstance(a.e2e_chunks, list) or a.e2e_chunks > 1:
+        chunks = HostPipeline.auto_chunks(W) if a.e2e_chunks == "auto" else a.e2e_chunks
+        chunks = list(chunks) if isinstance(chunks, (tuple, list)) else chunks
+        out["e2e_chunks"] = chunks
+        if isinstance(chunks, list) or chunks > 1:
             # the public end-to-end call: column blocks of the host state, so that copies and
             # kernels of different blocks overlap (batch.HostPipeline)
             bw.close()              # its scratch (~10 GB) is not needed any more
-            pipe = HostPipeline(model, W, chunks=a.e2e_chunks, device=bw.device, mode=a.e2e_mode,
+            pipe = HostPipeline(model, W, chunks=chunks, device=bw.device, mode=a.e2e_mode,
                                 compute_streams=a.e2e_compute_streams)
             for opt in (a.opt or []):
                 name, val = opt.split("=")
@@ -389,6 +393,8 @@ def measure(a, scen, model, w0, w1, rank, world_size, local, full):
         out["e2e"] = {"s_per_step": t_e2e/k_e2e, "h2d": h2d, "d2h": d2h, "steps": k_e2e}
         if pipe is not None:
             pipe.close()
+        else:
+            bw.close()
         del hg, hv, hf
     else:
         bw.close()
@@ -543,20 +549,22 @@ def run_ours(a):
     def e2e_obj(r):
         return {"value": r["worlds"]/(r["e2e_ms"]*1e-3), "unit": "world-steps/s",
                 "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
-                "steps": r["raw"]["e2e"]["steps"], "chunks": a.e2e_chunks, "mode": a.e2e_mode}
+                "steps": r["raw"]["e2e"]["steps"], "chunks": r["raw"].get("e2e_chunks"), "mode": a.e2e_mode}
     if "e2e" in m:
         out["e2e"] = e2e_obj(head)
+        ch = m.get("e2e_chunks")
+        nblocks = len(ch) if isinstance(ch, list) else ch
         out["e2e"]["how"] = (
             ("HostPipeline.step (%d column blocks of the pinned host state; %s): host -> "
              "device (gpos, gvel; constraint forces only for models whose forces are state), 1 step, "
              "device -> host (gpos, gvel, cforce), all blocks synchronised, every step; same "
              "staggered episodes as the timed region"
-             % (len(a.e2e_chunks) if isinstance(a.e2e_chunks, list) else a.e2e_chunks,
+             % (nblocks,
                 ("kernels of all blocks on %d streams, block after block, "
                  "arb_state_copy_host_strided copies on two more streams ordered by events"
                  % a.e2e_compute_streams) if a.e2e_mode == "serial"
                 else "arb_step_host_strided, one stream per block"))
-            if (isinstance(a.e2e_chunks, list) or a.e2e_chunks > 1) else
+            if nblocks > 1 else
             "arb_step_host: pinned host state -> device, 1 step, device -> host, "
             "synchronised, every step; same staggered episodes as the timed region")
     if other is not None:
