@@ -144,6 +144,10 @@ int arb_batch_set_stream(arb_batch *batch, void *stream);
  *                 bit-identical whatever the value;
  *  "gs_coop"      1: block-cooperative Gauss-Seidel kernel (sliding solves pooled through
  *                 shared memory) instead of the per-lane one; bit-identical results;
+ *  "prepare_group" 1: the prepare stage runs with a group of 16 lanes per world and the world's
+ *                 intermediates in shared memory (csrc/arb_group.cuh), the finish stage as
+ *                 q'+ = q_free + K y; same results to 1e-10 (other summation order), 5x slower than the
+ *                 default lane-per-world stages on human36: an A/B switch;
  *  "time_stages"  1: CUDA events around every fused stage, synchronising after every step -- a
  *                 diagnostic for bench.py, read with arb_batch_stage_ms; setting it clears the
  *                 accumulators */
