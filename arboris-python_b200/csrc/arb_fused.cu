@@ -68,24 +68,34 @@ __global__ void __launch_bounds__(FUSED_THREADS, PREP_MINBLOCKS) k_fused_prepare
   if (s >= b.W) return;
   world_fused_prepare(m, fused_tile_view(b, s), w, dt);
 }
-// threads per CTA of the Gauss-Seidel kernel.  At 255 registers per thread this also sets the
-// number of resident warps per SM (64: 8 warps, 96: 6, 160: 5, 224: 7): the stage re-reads the
-// same ~3.5 KB of operands per world in every sweep, and whether the worlds in flight fit the L2
-// between two sweeps matters more than thread-level parallelism (profiles/README.md, round 2).
-#ifndef GS_THREADS
-#define GS_THREADS FUSED_THREADS
+// Threads per CTA of the Gauss-Seidel kernel: 128 for large batches (8.87 ms against 9.01 with 64 and
+// 9.11 with 32 at 262144 worlds: fewer, fatter CTAs waste less of an SM while a CTA's last warp
+// finishes), 32 for batches of about one wave (2.35 against 2.40 ms at 32768 worlds).  At 255 registers
+// per thread all three keep 8 resident warps per SM; 96 / 160 / 224 threads (6 / 5 / 7 warps) are slower.
+#ifndef GS_L_SMEM_THREADS
+#define GS_L_SMEM_THREADS 128
 #endif
-__global__ void __launch_bounds__(GS_THREADS, GS_MINBLOCKS) k_fused_gs(DevModel m, DevBatch b, double dt) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, GS_MINBLOCKS) k_fused_gs(DevModel m, DevBatch b, double dt) {
   FUSED_SLOT_WORLD();
   if (s >= b.W) return;
 #if GS_L_SMEM
-  __shared__ double sL[36 * GS_THREADS];
-  const unsigned long long key = world_fused_gs(m, fused_tile_view(b, s), w, dt, sL + threadIdx.x, GS_THREADS);
+  __shared__ double sL[36 * THREADS];
+  const unsigned long long key = world_fused_gs(m, fused_tile_view(b, s), w, dt, sL + threadIdx.x, THREADS);
 #else
   double Lr[36];
   const unsigned long long key = world_fused_gs(m, fused_tile_view(b, s), w, dt, Lr, 1);
 #endif
   if (b.fkey != nullptr) b.fkey[s] = key;
+}
+static void launch_gs(const arb_batch* b, const DevBatch& d, double dt) {
+  const int64_t W = d.W;
+#ifdef GS_THREADS
+  k_fused_gs<GS_THREADS><<<(unsigned)((W + GS_THREADS - 1) / GS_THREADS), GS_THREADS, 0, b->stream>>>(b->m, d, dt);
+#else
+  if (W >= 98304) k_fused_gs<128><<<(unsigned)((W + 127) / 128), 128, 0, b->stream>>>(b->m, d, dt);
+  else k_fused_gs<32><<<(unsigned)((W + 31) / 32), 32, 0, b->stream>>>(b->m, d, dt);
+#endif
 }
 // block-cooperative Gauss-Seidel: the sliding-friction solves of a visit are pooled over the
 // block through shared memory (world_fused_gs_coop)
@@ -215,7 +225,12 @@ static int ensure_fused_scratch(arb_batch* b) {
   if (group_supported(b))
     CUDA_OKF(cudaFuncSetAttribute(k_fused_prepare_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem_bytes(b)));
   // the per-lane stages live on L1 (operands re-read every sweep / pass): no shared-memory carve-out
-  CUDA_OKF(cudaFuncSetAttribute(k_fused_gs, cudaFuncAttributePreferredSharedMemoryCarveout, GS_L_SMEM ? 20 : 0));
+#ifdef GS_THREADS
+  CUDA_OKF(cudaFuncSetAttribute(k_fused_gs<GS_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, GS_L_SMEM ? 20 : 0));
+#else
+  CUDA_OKF(cudaFuncSetAttribute(k_fused_gs<128>, cudaFuncAttributePreferredSharedMemoryCarveout, GS_L_SMEM ? 20 : 0));
+  CUDA_OKF(cudaFuncSetAttribute(k_fused_gs<32>, cudaFuncAttributePreferredSharedMemoryCarveout, GS_L_SMEM ? 20 : 0));
+#endif
   CUDA_OKF(cudaFuncSetAttribute(k_fused_prepare_lane, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   CUDA_OKF(cudaFuncSetAttribute(k_fused_finish, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   b->fused = f;
@@ -348,7 +363,7 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
         k_fused_gs_coop<<<(unsigned)((W + GS_COOP_THREADS - 1) / GS_COOP_THREADS), GS_COOP_THREADS,
                           GS_COOP_SMEM, b->stream>>>(b->m, d, dt);
       else
-        k_fused_gs<<<(unsigned)((W + GS_THREADS - 1) / GS_THREADS), GS_THREADS, 0, b->stream>>>(b->m, d, dt);
+        launch_gs(b, d, dt);
     }
     if (ev[0]) cudaEventRecord(ev[2], b->stream);
     if (grp) k_fused_finish_k<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, d, dt);
@@ -395,7 +410,7 @@ int arb_fused_step_half(arb_batch* b, double dt, int half) {
       k_fused_prepare_group<<<(unsigned)((W + GROUP_WPC - 1) / GROUP_WPC), GROUP_WPC * ARB_GL, group_smem_bytes(b), b->stream>>>(b->m, b->d, dt, 1);
     else
       k_fused_prepare_lane<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);
-    if (b->m.nc > 0) k_fused_gs<<<(unsigned)((W + GS_THREADS - 1) / GS_THREADS), GS_THREADS, 0, b->stream>>>(b->m, b->d, dt);
+    if (b->m.nc > 0) launch_gs(b, b->d, dt);
     b->launches += (b->m.nc > 0) ? 2 : 1;
   } else {
     if (b->half_group) k_fused_finish_k<<<g, FUSED_THREADS, 0, b->stream>>>(b->m, b->d, dt);

@@ -109,3 +109,44 @@ def test_human36_falling():
         y = np.einsum("wij,jk->wik", pose, bp1)[:, 1, 3]
         assert (y >= -1e-3).all(), (k, y)       # the reference asserts f.pose[1,3] >= 0 on its contact frames
     assert int(bw.constraints("active").sum()) >= 8
+
+
+def test_parameters_edited_between_steps_are_honoured():
+    """the reference reads controller / constraint parameters live at every step
+    (controllers.py:141-159, core.py:913).  Retarget a PD set-point and disable a constraint between
+    two steps of the single-world facade: each step must equal the oracle stepping a model flattened
+    AFTER the edit (and differ from the result without the edit)."""
+    import numpy as np
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from arboris_b200 import scenarios
+    from arboris_b200.flatten import flatten
+    from oracle.arboris_oracle import OracleWorld
+    w = scenarios.zoo_world()
+    dt = 1e-3
+
+    def oracle_step():
+        m = flatten(w)
+        o = OracleWorld(m.to_dict())
+        o.step(dt)
+        return o.gvel.copy()
+
+    def facade_step():
+        w.update_dynamic()
+        w.update_controllers(dt)
+        w.update_constraints(dt)
+        w.integrate(dt)
+        return w.gvel.copy()
+
+    ref = oracle_step()
+    got = facade_step()
+    assert np.abs(got - ref).max() <= 1e-10*max(1., np.abs(ref).max())
+    pd = [c for c in w._controllers if type(c).__name__ == "ProportionalDerivativeController"][0]
+    pd.gpos_des[:] = pd.gpos_des + 0.4                      # retarget between steps
+    w._constraints[0].disable()
+    ref2 = oracle_step()
+    got2 = facade_step()
+    assert np.abs(got2 - ref2).max() <= 1e-10*max(1., np.abs(ref2).max())
+    pd.gpos_des[:] = pd.gpos_des - 0.4                      # and the edit mattered
+    assert np.abs(oracle_step() - ref2).max() > 1e-6
