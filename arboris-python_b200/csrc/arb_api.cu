@@ -1,5 +1,6 @@
 // C ABI of arboris_b200 (include/arboris_b200.h) and the lane-per-world kernels.
-// sm_100a, fp64.  The warp-per-world fused step lives in arb_fused.cu.
+// sm_100a, fp64.  The fused step (lane-per-world stages, and the 16-lanes-per-world prepare stage of
+// arb_group.cuh) lives in arb_fused.cu.
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstring>
@@ -300,7 +301,7 @@ extern "C" int arb_integrate(arb_batch* b, double dt) {
 }
 
 // nsteps of the simulate() loop through the four phase kernels (used when the
-// fused warp-per-world kernel does not support the model, and by tests).
+// fused stages do not support the model, and by tests).
 int arb_step_phases(arb_batch* b, const double* dts, int nsteps) {
   int rc = arb_ensure_phase_scratch(b); if (rc) return rc;
   const unsigned g = lpw_grid(b->d.W);

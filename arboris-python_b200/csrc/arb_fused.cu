@@ -72,9 +72,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, PREP_MINBLOCKS) k_fused_prepare
 // 9.11 with 32 at 262144 worlds: fewer, fatter CTAs waste less of an SM while a CTA's last warp
 // finishes), 32 for batches of about one wave (2.35 against 2.40 ms at 32768 worlds).  At 255 registers
 // per thread all three keep 8 resident warps per SM; 96 / 160 / 224 threads (6 / 5 / 7 warps) are slower.
-#ifndef GS_L_SMEM_THREADS
-#define GS_L_SMEM_THREADS 128
-#endif
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, GS_MINBLOCKS) k_fused_gs(DevModel m, DevBatch b, double dt) {
   FUSED_SLOT_WORLD();

@@ -42,7 +42,7 @@ struct arb_batch {
 const char* arb_set_error(const std::string& s);
 int arb_step_phases(arb_batch* b, const double* dts, int nsteps);
 int arb_ensure_phase_scratch(arb_batch* b);
-// warp-per-world fused step (arb_fused.cu)
+// fused step (arb_fused.cu)
 bool arb_fused_supported(const arb_batch* b);
 int arb_fused_step(arb_batch* b, const double* dts, int nsteps);
 void arb_fused_release(arb_batch* b);
