@@ -68,10 +68,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, PREP_MINBLOCKS) k_fused_prepare
   if (s >= b.W) return;
   world_fused_prepare(m, fused_tile_view(b, s), w, dt);
 }
-// Threads per CTA of the Gauss-Seidel kernel: 128 for large batches (8.87 ms against 9.01 with 64 and
-// 9.11 with 32 at 262144 worlds: fewer, fatter CTAs waste less of an SM while a CTA's last warp
-// finishes), 32 for batches of about one wave (2.35 against 2.40 ms at 32768 worlds).  At 255 registers
-// per thread all three keep 8 resident warps per SM; 96 / 160 / 224 threads (6 / 5 / 7 warps) are slower.
+// Threads per CTA of the Gauss-Seidel kernel: 128 (8.87 ms against 9.01 with 64 and 9.11 with 32 at
+// 262144 worlds; end to end, with seven column blocks on three streams, 1.406e7 world-steps/s against
+// 1.37e7 / 1.36e7: fewer, fatter CTAs waste less of an SM while a CTA's last warp finishes).  At 255
+// registers per thread all three keep 8 resident warps per SM; 96 / 160 / 224 threads (6 / 5 / 7 warps)
+// are slower.  GS_THREADS builds another size (A/B).
+#ifndef GS_THREADS
+#define GS_THREADS 128
+#endif
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, GS_MINBLOCKS) k_fused_gs(DevModel m, DevBatch b, double dt) {
   FUSED_SLOT_WORLD();
@@ -87,12 +91,7 @@ __global__ void __launch_bounds__(THREADS, GS_MINBLOCKS) k_fused_gs(DevModel m, 
 }
 static void launch_gs(const arb_batch* b, const DevBatch& d, double dt) {
   const int64_t W = d.W;
-#ifdef GS_THREADS
   k_fused_gs<GS_THREADS><<<(unsigned)((W + GS_THREADS - 1) / GS_THREADS), GS_THREADS, 0, b->stream>>>(b->m, d, dt);
-#else
-  if (W >= 98304) k_fused_gs<128><<<(unsigned)((W + 127) / 128), 128, 0, b->stream>>>(b->m, d, dt);
-  else k_fused_gs<32><<<(unsigned)((W + 31) / 32), 32, 0, b->stream>>>(b->m, d, dt);
-#endif
 }
 // block-cooperative Gauss-Seidel: the sliding-friction solves of a visit are pooled over the
 // block through shared memory (world_fused_gs_coop)
@@ -222,12 +221,7 @@ static int ensure_fused_scratch(arb_batch* b) {
   if (group_supported(b))
     CUDA_OKF(cudaFuncSetAttribute(k_fused_prepare_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem_bytes(b)));
   // the per-lane stages live on L1 (operands re-read every sweep / pass): no shared-memory carve-out
-#ifdef GS_THREADS
   CUDA_OKF(cudaFuncSetAttribute(k_fused_gs<GS_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, GS_L_SMEM ? 20 : 0));
-#else
-  CUDA_OKF(cudaFuncSetAttribute(k_fused_gs<128>, cudaFuncAttributePreferredSharedMemoryCarveout, GS_L_SMEM ? 20 : 0));
-  CUDA_OKF(cudaFuncSetAttribute(k_fused_gs<32>, cudaFuncAttributePreferredSharedMemoryCarveout, GS_L_SMEM ? 20 : 0));
-#endif
   CUDA_OKF(cudaFuncSetAttribute(k_fused_prepare_lane, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   CUDA_OKF(cudaFuncSetAttribute(k_fused_finish, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   b->fused = f;
