@@ -35,6 +35,7 @@ struct FusedState {
   int64_t steps = 0;
   double* pstate = nullptr;                   // private state by slot: gpos, gvel, cforce
   int* pstatus = nullptr;                     // status bits by slot, merged into the caller's on scatter
+  bool has_K = false;                         // the scratch holds K = Z^-1 G^T (group prepare stage only: 4.7 KB per human36 world)
 };
 
 #define CUDA_OKF(call)                                                            \
@@ -197,6 +198,8 @@ static int ensure_fused_scratch(arb_batch* b) {
   FusedSizes s = fused_sizes(b->model->host);
   const int64_t W = fused_padded_worlds(b->d.W);
   FusedState* f = new FusedState();
+  f->has_K = b->prepare_group != 0;           // (the option must be set before the first step)
+  if (!f->has_K) s.fK = 0;
   CUDA_OKF(cudaMalloc((void**)&f->dbl, sizeof(double) * s.total_doubles() * W));
   CUDA_OKF(cudaMalloc((void**)&f->ints, sizeof(int) * s.total_ints() * W));
   CUDA_OKF(cudaMemsetAsync(f->dbl, 0, sizeof(double) * s.total_doubles() * W, b->stream));
@@ -350,6 +353,10 @@ int arb_fused_step(arb_batch* b, const double* dts, int nsteps) {
       priv_valid = true;
     }
     const bool grp = b->prepare_group && group_supported(b);
+    if (grp && !f->has_K) {
+      arb_set_error("set the prepare_group option before the batch's first step (its scratch has no room for K)");
+      return leave(-3);
+    }
     b->poses_valid = grp ? 0 : 1;      // (the group stage keeps poses on chip unless asked: arb_step_begin)
     if (ev[0]) cudaEventRecord(ev[0], b->stream);
     if (grp)
@@ -402,6 +409,10 @@ int arb_fused_step_half(arb_batch* b, double dt, int half) {
     f->inv_valid = false;
   }
   const bool grp = b->prepare_group && group_supported(b);
+  if (grp && !f->has_K) {
+    arb_set_error("set the prepare_group option before the batch's first step (its scratch has no room for K)");
+    return -3;
+  }
   if (half == 0) {
     b->half_group = grp ? 1 : 0;       // the finish half must match the prepare half
     b->poses_valid = 1;

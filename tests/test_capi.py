@@ -50,6 +50,45 @@ def test_model_create_validates_without_gpu(lib):
     assert lib.arb_model_create(None, C.byref(h)) < 0
 
 
+def test_model_create_validates_controller_and_limit_tables(lib):
+    """descriptor contents that come through the public ABI are checked before any
+    kernel can index with them: PD blob offset / size, its dof and gpos maps, and the dof / gpos index a
+    JointLimits row carries for its joint.  Plus the per-world PD parameter rows the ABI reports."""
+    from arboris_b200 import _capi
+    model, _ = load_golden("zoo")
+    h = C.c_void_p()
+
+    def create(**edit):
+        import copy
+        m = copy.copy(model)
+        for k, v in edit.items():
+            setattr(m, k, v)
+        desc, keep = _capi.make_desc(m)
+        rc = lib.arb_model_create(C.byref(desc), C.byref(h))
+        return rc, lib.arb_last_error()
+
+    rc, _ = create()
+    assert rc == 0
+    dofs = (C.c_int32*16)()
+    npd = lib.arb_model_pd_dofs(h, dofs, 16)
+    assert npd == 5 and sorted(dofs[i] for i in range(npd)) == sorted(set(dofs[i] for i in range(npd)))
+    lib.arb_model_destroy(h)
+    pd = [a for a in range(len(model.ctrl_type)) if int(model.ctrl_type[a]) == 1][0]
+    ci = np.array(model.ctrl_int, dtype=np.int32).copy()
+    ci[pd][1] = int(np.asarray(model.ctrl_blob).size) - 2          # blob offset past the end
+    rc, msg = create(ctrl_int=ci)
+    assert rc < 0 and b"blob" in msg
+    blob = np.array(model.ctrl_blob, dtype=float).copy()
+    blob[int(model.ctrl_int[pd][1])] = 10_000.                      # dof map entry out of range
+    rc, msg = create(ctrl_blob=blob)
+    assert rc < 0 and b"out of range" in msg
+    lim = [c for c in range(len(model.cons_type)) if int(model.cons_type[c]) == 0][0]
+    ki = np.array(model.cons_int, dtype=np.int32).copy()
+    ki[lim][1] += 1                                                  # dof index that is not the joint's
+    rc, msg = create(cons_int=ki)
+    assert rc < 0 and b"JointLimits" in msg
+
+
 def test_step_without_gpu_fails_loudly():
     """No CUDA device -> the product raises; it never falls back to a CPU path."""
     import torch
