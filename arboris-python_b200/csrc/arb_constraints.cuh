@@ -237,11 +237,16 @@ ARB_NOINLINE void softfinger_sliding(const double* A, const double* alpha, doubl
   // is badly scaled.
   double B[9];
   const double idn = 1. / A[15];
+  double ie2[3] = {1., 1., 1.};          // eps^-2; with eps = 1 (constraints.py:423) s * 1 is s: no division
+  if (!unit_eps) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) ie2[i] = 1. / (eps[i] * eps[i]);
+  }
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
     for (int j = 0; j < 3; ++j)
-      B[3 * i + j] = (A[4 * i + j] - ((i == j) ? s * (1. / (eps[i] * eps[i])) : 0.)) - (A[4 * i + 3] * idn) * A[12 + j];
+      B[3 * i + j] = (A[4 * i + j] - ((i == j) ? s * ie2[i] : 0.)) - (A[4 * i + 3] * idn) * A[12 + j];
   const double rhs[3] = {-alpha[0] + (A[3] * idn) * alpha[3], -alpha[1] + (A[7] * idn) * alpha[3],
                          -alpha[2] + (A[11] * idn) * alpha[3]};
   const double c00 = B[4] * B[8] - B[5] * B[7], c01 = B[5] * B[6] - B[3] * B[8], c02 = B[3] * B[7] - B[4] * B[6];
