@@ -516,16 +516,22 @@ ARB_HD int poly6_largest_root_fast(const double* p, double* root) {
 ARB_HD bool sliding_root_structured(const double* A, const double* alpha, double mu, double* s_out, bool* found) {
   const double Yc[3] = {A[3], A[7], A[11]};
   const double yn = A[15];
-  const double a = mu / yn * alpha[3];
+  // one reciprocal of y_n and one of a instead of five divisions (the reference divides: mu/y_n*alpha_n
+  // ...; the operands of B move by an ulp, its admissible root by that much times its conditioning --
+  // far inside the 1e-14 at which the root agrees with LAPACK's anyway)
+  const double iyn = 1. / yn;
+  const double mu_yn = mu * iyn, an_yn = alpha[3] * iyn;
+  const double a = mu_yn * alpha[3];
   double beta[3], bb[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) {
-    beta[i] = alpha[i] - alpha[3] / yn * Yc[i];
-    bb[i] = mu / yn * Yc[i];
+    beta[i] = alpha[i] - an_yn * Yc[i];
+    bb[i] = mu_yn * Yc[i];
   }
-  const double kappa = (Yc[0] * Yc[0] + Yc[1] * Yc[1] + Yc[2] * Yc[2]) / yn;
-  const double cc = 2. / a * (beta[0] * bb[0] + beta[1] * bb[1] + beta[2] * bb[2]);
-  const double al = -((beta[0] * beta[0] + beta[1] * beta[1] + beta[2] * beta[2]) / (a * a));
+  const double kappa = (Yc[0] * Yc[0] + Yc[1] * Yc[1] + Yc[2] * Yc[2]) * iyn;
+  const double ia = 1. / a;
+  const double cc = 2. * ia * (beta[0] * bb[0] + beta[1] * bb[1] + beta[2] * bb[2]);
+  const double al = -((beta[0] * beta[0] + beta[1] * beta[1] + beta[2] * beta[2]) * (ia * ia));
   const double ga = (bb[0] * bb[0] + bb[1] * bb[1] + bb[2] * bb[2]) - 1.;
   const double delta = al * ga;
   double Q[9];
@@ -577,15 +583,17 @@ ARB_HD bool sliding_root_structured(const double* A, const double* alpha, double
   }
   if (!(fabs(p[6] - 1.) < 1e-9)) return false;
   p[6] = 1.;
-  double T = 0.;
-#pragma unroll
-  for (int k = 0; k < 6; ++k) T = fmax(T, fabs(p[k]));
-  T += 1.;
-  if (!(T < 1e300)) return false;
   double t;
   if (poly6_largest_root_fast(p, &t)) {
     if (t < 0.) { *found = false; *s_out = 0.; return true; }   // every real eigenvalue is > 0
   } else {
+    // (Cauchy bound of the roots, needed by the rigorous isolation only: the fast path rejects
+    // non-finite coefficients by itself -- its variance test fails on a NaN)
+    double T = 0.;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) T = fmax(T, fabs(p[k]));
+    T += 1.;
+    if (!(T < 1e300)) return false;
     double roots[6];
     const int nr = poly6_roots_slow(p, T, roots);
     if (nr == 0) { *found = false; *s_out = 0.; return true; }
