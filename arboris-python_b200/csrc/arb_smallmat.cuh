@@ -449,6 +449,9 @@ ARB_NOINLINE int poly6_roots_slow(const double* p, double T, double* roots) { re
 static long arb_fastroot_hits = 0;   // host unit tests only: how often the fast path certified its root
 static long arb_fastroot_fail[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // ... and why it did not (by exit), [7] = Laguerre iterations
 #endif
+#ifndef ARB_SIGMA_SUM
+#define ARB_SIGMA_SUM 1
+#endif
 #ifndef ARB_LAGUERRE_FAST
 #define ARB_LAGUERRE_FAST 1
 #endif
@@ -546,6 +549,19 @@ ARB_HD bool sliding_root_structured(const double* A, const double* alpha, double
   const double ga = (bb[0] * bb[0] + bb[1] * bb[1] + bb[2] * bb[2]) - 1.;
   const double delta = al * ga;
   double Q[9];
+#if ARB_SIGMA_SUM
+  // scale of the matrix polynomial: any sigma within a small factor of max(|Q_ij| + |c|, sqrt|delta|)
+  // serves (it only keeps the sextic's coefficients O(1)); the sum of the magnitudes costs ten additions
+  // where nine fp64 maxima cost sixty instructions
+  double sigma = sqrt(fabs(delta)) + fabs(cc);
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      Q[3 * i + j] = A[4 * i + j] - kappa;
+      sigma += fabs(Q[3 * i + j]);
+    }
+#else
   double sigma = sqrt(fabs(delta));
 #pragma unroll
   for (int i = 0; i < 3; ++i)
@@ -554,6 +570,7 @@ ARB_HD bool sliding_root_structured(const double* A, const double* alpha, double
       Q[3 * i + j] = A[4 * i + j] - kappa;
       sigma = fmax(sigma, fabs(Q[3 * i + j]) + fabs(cc));
     }
+#endif
   if (!(sigma > 0.) || !(sigma < 1e300)) return false;
   // scaled coefficients of  M(t) = t^2 I + t C1 + C0,  s = -sigma t
   const double is = 1. / sigma;
