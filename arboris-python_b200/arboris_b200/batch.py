@@ -12,6 +12,7 @@ State tensors (fp64, device, world index fastest -- the layout the kernels
 coalesce on):  ``gpos`` (ngpos, W), ``gvel`` (ndof, W), ``cforce`` (nrows, W).
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -388,7 +389,14 @@ class HostPipeline(object):
         self.ranges = block_ranges(self.nworlds, chunks)
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         serial = mode == "serial"
-        self._css = [torch.cuda.Stream(dev) for _ in range(max(1, int(compute_streams)))] if serial else None
+        ncs = max(1, int(compute_streams))
+        # ARB_B200_E2E_PRIO=1 (experiment): one compute stream per block, earlier blocks at higher
+        # priority, so that the blocks run nearly in order and a block's tail is filled by the next one
+        if serial and os.environ.get("ARB_B200_E2E_PRIO") == "1":
+            ncs = len(self.ranges)
+            self._css = [torch.cuda.Stream(dev, priority=max(-5, -(ncs - 1 - i))) for i in range(ncs)]
+        else:
+            self._css = [torch.cuda.Stream(dev) for _ in range(ncs)] if serial else None
         self._hs = torch.cuda.Stream(dev) if serial else None            # host -> device copies
         self._ds = torch.cuda.Stream(dev) if serial else None            # device -> host copies
         first = BatchedWorld(world_or_model, self.ranges[0][1] - self.ranges[0][0], device=dev,

@@ -55,6 +55,12 @@ struct FusedState {
 #ifndef PREP_MINBLOCKS
 #define PREP_MINBLOCKS 1    /* resident-CTA floor of the prepare kernel: 4 = 255 registers, 6 = 168, 8 = 128 */
 #endif
+#ifndef GS_STAGE_CARVEOUT
+#define GS_STAGE_CARVEOUT 40   /* per cent of the SM's 228 KB for shared memory: 2 CTAs x 43 KB (A/B builds) */
+#endif
+#ifndef GS_CARVEOUT
+#define GS_CARVEOUT 0          /* the unstaged kernel uses no shared memory (A/B builds: what a smaller L1 costs) */
+#endif
 #ifndef GS_MINBLOCKS
 #define GS_MINBLOCKS 1
 #endif
@@ -98,9 +104,43 @@ __global__ void __launch_bounds__(THREADS, GS_MINBLOCKS) k_fused_gs(DevModel m, 
 #endif
   if (b.fkey != nullptr) b.fkey[s] = key;
 }
+// Gauss-Seidel with the contact operands staged by TMA (world_fused_gs_staged): 10 KB of shared memory
+// and one mbarrier per warp, a 64-byte descriptor per constraint
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, GS_MINBLOCKS) k_fused_gs_staged(DevModel m, DevBatch b, double dt) {
+  __shared__ __align__(128) double sbuf[(THREADS / 32) * (GS_STAGE_WARP_BYTES / 8)];
+  __shared__ __align__(16) GsDesc sdesc[32];
+  __shared__ __align__(8) unsigned long long sbar[THREADS / 32];
+  const unsigned lane = threadIdx.x & 31u, wp = threadIdx.x >> 5;
+  GsStage st;
+  st.buf = sbuf + wp * (GS_STAGE_WARP_BYTES / 8);
+  st.buf_s = (unsigned)__cvta_generic_to_shared(st.buf);
+  st.bar_s = (unsigned)__cvta_generic_to_shared(&sbar[wp]);
+  st.parity = 0u;
+  st.tsel = 0u;
+  st.lane = lane;
+  st.desc = sdesc;
+  if (lane == 0u) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st.bar_s) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if ((int)threadIdx.x < m.nc) gs_desc_fill(m, sdesc, threadIdx.x);
+  __syncthreads();
+  FUSED_SLOT_WORLD();
+  (void)w;
+  const bool valid = s < b.W;
+  const int64_t sv = valid ? s : b.W - 1;
+  double Lr[36];
+  const unsigned long long key = world_fused_gs_staged(m, fused_tile_view(b, sv), sv, valid, dt, Lr, 1, st);
+  if (valid && b.fkey != nullptr) b.fkey[s] = key;
+}
 static void launch_gs(const arb_batch* b, const DevBatch& d, double dt) {
   const int64_t W = d.W;
-  k_fused_gs<GS_THREADS><<<(unsigned)((W + GS_THREADS - 1) / GS_THREADS), GS_THREADS, 0, b->stream>>>(b->m, d, dt);
+  const unsigned grid = (unsigned)((W + GS_THREADS - 1) / GS_THREADS);
+  if (b->gs_stage && b->m.nc <= 32)
+    k_fused_gs_staged<GS_THREADS><<<grid, GS_THREADS, 0, b->stream>>>(b->m, d, dt);
+  else
+    k_fused_gs<GS_THREADS><<<grid, GS_THREADS, 0, b->stream>>>(b->m, d, dt);
 }
 // block-cooperative Gauss-Seidel: the sliding-friction solves of a visit are pooled over the
 // block through shared memory (world_fused_gs_coop)
@@ -232,7 +272,9 @@ static int ensure_fused_scratch(arb_batch* b) {
   if (group_supported(b))
     CUDA_OKF(cudaFuncSetAttribute(k_fused_prepare_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem_bytes(b)));
   // the per-lane stages live on L1 (operands re-read every sweep / pass): no shared-memory carve-out
-  CUDA_OKF(cudaFuncSetAttribute(k_fused_gs<GS_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, GS_L_SMEM ? 20 : 0));
+  CUDA_OKF(cudaFuncSetAttribute(k_fused_gs<GS_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, GS_L_SMEM ? 20 : GS_CARVEOUT));
+  // (staged: 2 CTAs x 43 KB per SM; the driver rounds the carve-out up to the next configuration)
+  CUDA_OKF(cudaFuncSetAttribute(k_fused_gs_staged<GS_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, GS_STAGE_CARVEOUT));
   CUDA_OKF(cudaFuncSetAttribute(k_fused_prepare_lane, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   CUDA_OKF(cudaFuncSetAttribute(k_fused_finish, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   b->fused = f;

@@ -391,6 +391,108 @@ ARB_D void gs_cache_load(const DevModel& m, const DevBatch& b, int64_t w, GsCach
   }
 }
 
+// Block switch F -> G in one memory round trip (used by the staged Gauss-Seidel).  gs_cache_flush
+// followed by gs_cache_load is a chain of three: the flush loads Lambda[r, F] and u[r] of the outside
+// rows, stores u[r], and the load then reads the u rows of G back through the L2 (and only then asks
+// for Lambda_GG) -- ncu: ~3 000 cycles per switch, showing up at the first use of the new block's u.
+// Here the new block's rows are updated in registers and handed over directly (their memory copy is
+// not read while the block is cached, and is rewritten when it leaves), Lambda_GG is requested before
+// anything else, and the remaining outside rows follow.  Same arithmetic per row, same bits.
+ARB_D void gs_cache_switch(const DevModel& m, const DevBatch& b, int64_t w, GsCache& k, int g2, int n2) {
+  if (k.g < 0 || g2 < 0) {
+    gs_cache_flush(m, b, w, k);
+    if (g2 >= 0) gs_cache_load<true>(m, b, w, k, g2, n2);
+    return;
+  }
+  const int NG = m.ngrows, g = k.g, n = k.n;
+  const int rowstride = NG * ARB_TILE;
+  bool any = false;
+#pragma unroll
+  for (int p = 0; p < 6; ++p) any = any || (p < n && k.dy[p] != 0.);
+  double un[6];
+  const double* pun = b.fu + g2 * ARB_TILE;
+  const double* plg = b.fLam + (g2 * NG + g2) * ARB_TILE;      // Lambda[g2 + p, g2 + q]
+  const double* plf = b.fLam + (g2 * NG + g) * ARB_TILE;       // Lambda[g2 + p, g + q]
+  double* pu = b.fu + g * ARB_TILE;
+  if (n2 == 6) {
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      un[p] = pun[p * ARB_TILE];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) GSL(k, 6 * p + q) = plg[p * rowstride + q * ARB_TILE];
+    }
+    if (any) {
+      if (n == 6) {
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+          double a = 0.;
+#pragma unroll
+          for (int q = 0; q < 6; ++q) a += plf[p * rowstride + q * ARB_TILE] * k.dy[q];
+          un[p] = un[p] + a;
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < 6; ++p) un[p] = un[p] + plf[p * rowstride] * k.dy[0];
+      }
+    }
+  } else {
+    un[0] = pun[0];
+#pragma unroll
+    for (int p = 1; p < 6; ++p) un[p] = 0.;
+    GSL(k, 0) = plg[0];
+    if (any) {
+      if (n == 6) {
+        double a = 0.;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) a += plf[q * ARB_TILE] * k.dy[q];
+        un[0] = un[0] + a;
+      } else {
+        un[0] = un[0] + plf[0] * k.dy[0];
+      }
+    }
+  }
+  if (any) {     // the rows outside both blocks, as in gs_cache_flush
+    const double* pl = b.fLam + g * ARB_TILE;
+    const int nrest = NG - n - n2;
+    const int lo = g < g2 ? g : g2, nlo = g < g2 ? n : n2, hi = g < g2 ? g2 : g, nhi = g < g2 ? n2 : n;
+#pragma unroll 1
+    for (int i0 = 0; i0 < nrest; i0 += 4) {
+      double acc[4], uu[4];
+      int rr[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int r = i0 + i < nrest ? i0 + i : nrest - 1;
+        if (r >= lo) r += nlo;
+        if (r >= hi) r += nhi;
+        rr[i] = r;
+        const double* q = pl + r * rowstride;
+        uu[i] = b.fu[r * ARB_TILE];
+        if (n == 6) {
+          double a = 0.;
+#pragma unroll
+          for (int p = 0; p < 6; ++p) a += q[p * ARB_TILE] * k.dy[p];
+          acc[i] = uu[i] + a;
+        } else {
+          acc[i] = uu[i] + q[0] * k.dy[0];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i0 + i < nrest) b.fu[rr[i] * ARB_TILE] = acc[i];
+    }
+  }
+  if (n == 6) {
+#pragma unroll
+    for (int p = 0; p < 6; ++p) pu[p * ARB_TILE] = k.u[p];
+  } else {
+    pu[0] = k.u[0];
+  }
+#pragma unroll
+  for (int p = 0; p < 6; ++p) { k.u[p] = un[p]; k.dy[p] = 0.; }
+  k.g = g2;
+  k.n = n2;
+}
+
 // one visit of a constraint that touches TWO generator bodies (e.g. a ball-and-socket joint
 // between two moving bodies): everything through memory.
 ARB_NOINLINE void gs_visit_two_body(const DevModel& m, const DevBatch& b, int64_t w, int c, double dt, int* status) {
@@ -934,6 +1036,337 @@ ARB_D unsigned long long world_fused_gs(const DevModel& m, const DevBatch& b, in
   if (status) b.status[w] |= status;
   return gs_sort_key(m, slid, amask);
 }
+
+// ---------------------------------------------------------------------------------------
+// Gauss-Seidel with the contact operands staged in shared memory by TMA (device only).
+//
+// Same arithmetic, same order as world_fused_gs above.  What changes is where a contact visit finds
+// its operands.  In world_fused_gs the 4x4 Delassus block A_cc, its pseudo-inverse, the contact map
+// and sdist are ~35 global loads per lane that the L1 prefetch of the previous visit brings no closer
+// than the L2 (ncu: their first uses hold a quarter of the stage's stall samples).  Here
+//  * the warp walks the (sweep, constraint) sequence in lockstep over a warp-uniform schedule (the
+//    constraints SOME world of the warp visits; the active sets do not change during the sweeps, so
+//    the schedule is a bit mask formed once) -- lanes whose world does not take part in a visit idle;
+//  * the tile layout [W/32][elem][32] makes A_cc, pinv(A_cc), t_c and (sdist, sdist/dt) of the warp's
+//    32 worlds contiguous blocks (4 KB, 4 KB, 768 B, 512 B), which one elected lane copies into the
+//    warp's shared-memory buffer with cp.async.bulk (TMA, completion on the warp's mbarrier) as soon
+//    as every lane has read the operands of the current visit -- before the sliding solves of that
+//    visit, one whole visit ahead of their use, holding no registers;
+//  * the per-constraint model tables (type, rows, generator block, friction) are one 64-byte record
+//    per constraint in shared memory instead of eight dependent look-ups through the L1.
+#ifdef __CUDACC__
+#ifndef GS_STAGE_PF_F
+#define GS_STAGE_PF_F 0
+#endif
+#ifndef GS_STAGE_SWITCH
+#define GS_STAGE_SWITCH 0     /* 0: flush, then load; 1: one round trip (gs_cache_switch); 2: Lambda_GG requested before the flush (A/B builds) */
+#endif
+struct GsDesc {           // one constraint, as the sweep loop needs it (shared memory, filled once per CTA)
+  int type, g1, g0, row;
+  int aligned, gneed, nneed, staged;
+  double mu, eps[3];
+};
+#define GS_STAGE_AP_BYTES (2 * 16 * ARB_TILE * 8)      /* A_cc, pinv(A_cc) */
+#define GS_STAGE_T_BYTES (3 * ARB_TILE * 8)            /* t_c of an aligned contact, double-buffered */
+#define GS_STAGE_AUX_BYTES (2 * ARB_TILE * 8)          /* sdist, sdist / dt */
+#define GS_STAGE_WARP_BYTES (GS_STAGE_AP_BYTES + 2 * GS_STAGE_T_BYTES + GS_STAGE_AUX_BYTES)
+struct GsStage {
+  double* buf;          // the warp's staging buffer: A (16 rows of 32 lanes), P (16), aux (2), T (2 x 3)
+  unsigned buf_s;       // ... its shared-space address
+  unsigned bar_s;       // shared-space address of the warp's mbarrier (one arrival per refill)
+  unsigned parity;      // phase the next wait looks for (warp-uniform)
+  unsigned tsel;        // which T buffer the CURRENT visit reads (warp-uniform)
+  unsigned lane;
+  const GsDesc* desc;   // [nc] in shared memory
+};
+__device__ __forceinline__ void gs_bulk_g2s(unsigned dst_s, const double* src, unsigned bytes, unsigned bar_s) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_s), "l"(src), "r"(bytes), "r"(bar_s) : "memory");
+}
+// refill for constraint c; tnext: the T buffer the visit of c will read
+__device__ __forceinline__ void gs_stage_issue(const GsStage& st, const DevBatch& b, int c, unsigned tnext) {
+  // b is the issuing lane's view of its tile: lane 0's element is st.lane doubles below
+  const GsDesc& d = st.desc[c];
+  const unsigned tb = d.aligned ? (unsigned)GS_STAGE_T_BYTES : 0u;
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+               ::"r"(st.bar_s), "r"((unsigned)(GS_STAGE_AP_BYTES + GS_STAGE_AUX_BYTES) + tb) : "memory");
+  gs_bulk_g2s(st.buf_s, b.fAcc + d.row * (4 * ARB_TILE) - st.lane, 16 * ARB_TILE * 8, st.bar_s);
+  gs_bulk_g2s(st.buf_s + 16 * ARB_TILE * 8, b.fP + d.row * (4 * ARB_TILE) - st.lane, 16 * ARB_TILE * 8, st.bar_s);
+  gs_bulk_g2s(st.buf_s + GS_STAGE_AP_BYTES, b.faux + c * (4 * ARB_TILE) - st.lane, GS_STAGE_AUX_BYTES, st.bar_s);
+  if (d.aligned)
+    gs_bulk_g2s(st.buf_s + GS_STAGE_AP_BYTES + GS_STAGE_AUX_BYTES + tnext * GS_STAGE_T_BYTES,
+                (d.g1 < 0 ? b.fT0 : b.fT1) + c * (24 * ARB_TILE) - st.lane, GS_STAGE_T_BYTES, st.bar_s);
+}
+__device__ __forceinline__ void gs_stage_wait(const GsStage& st) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "GS_STAGE_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra GS_STAGE_WAIT_%=;\n"
+      "}\n" ::"r"(st.bar_s), "r"(st.parity) : "memory");
+}
+
+// SoftFingerContact.solve up to the sliding solve (softfinger_solve_tiled, first part): returns 1
+// (separating), 2 (static) with f, df updated, or 3 with the sliding problem (A, alpha) copied out of
+// the staging buffer -- the caller releases the buffer, then solves.
+__device__ __forceinline__ int softfinger_begin_tiled(const double* v, const double* pA, const double* pP, double sdist,
+                                                      double sd_dt, double mu, const double* eps, double dt, double* f,
+                                                      double* df, double* A, double* alpha) {
+  double vnf3;
+  {
+    double t = 0.;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t += pA[(12 + j) * ARB_TILE] * f[j];
+    vnf3 = v[3] - t;
+  }
+  if (sdist + dt * vnf3 > 0.) {  // separating: release
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { df[i] = -f[i]; f[i] = 0.; }
+    return 1;
+  }
+  const double rhs[4] = {v[0], v[1], v[2], v[3] + sd_dt};
+  double nf[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double t = 0.;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t += -pP[(4 * i + j) * ARB_TILE] * rhs[j];
+    df[i] = t;
+    nf[i] = f[i] + t;
+  }
+  double lhs = 0.;
+  if (eps[0] == 1. && eps[1] == 1. && eps[2] == 1.) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) lhs += nf[i] * nf[i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { const double t = nf[i] / eps[i]; lhs += t * t; }
+  }
+  const double rr = nf[3] * mu;
+  if (lhs <= rr * rr) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) f[i] = nf[i];
+    return 2;
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) A[i] = pA[i * ARB_TILE];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double t = 0.;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) t += A[4 * i + j] * f[j];
+    alpha[i] = v[i] - t;
+  }
+  alpha[3] = vnf3 + sd_dt;
+  return 3;
+}
+
+// gs_visit_one_body<4> with staged operands.  vmask: the lanes of the warp that take part in this
+// visit (all of them are here); cn: the warp's next staged contact (-1: none left).
+__device__ __forceinline__ int gs_visit_contact_staged(const DevBatch& b, int c, double dt, GsCache& k, int* status,
+                                                       const GsStage& st, unsigned vmask, int cn) {
+  const GsDesc& d = st.desc[c];
+  const bool side0 = d.g1 < 0;
+  const double* Tg = (side0 ? b.fT0 : b.fT1) + c * (24 * ARB_TILE);
+  const double sign = side0 ? -1. : 1.;
+  double* pf = b.ff + d.row * ARB_TILE;
+  const bool al = d.aligned != 0;
+  const double* sA = st.buf + st.lane;
+  const double* sP = sA + 16 * ARB_TILE;
+  const double* sAux = sA + 32 * ARB_TILE;
+  const double* sT = sA + 34 * ARB_TILE + st.tsel * (3 * ARB_TILE);
+  double v[4], f[4], df[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) f[i] = pf[i * ARB_TILE];
+  gs_stage_wait(st);
+  if (al) {
+    gs_aligned_rows(sT, k.u, v);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double acc = 0.;
+#pragma unroll
+      for (int p = 0; p < 6; ++p) acc += Tg[(i * 6 + p) * ARB_TILE] * k.u[p];
+      v[i] = sign * acc;
+    }
+  }
+  double A[16], alpha[4];
+  int br = softfinger_begin_tiled(v, sA, sP, sAux[0], sAux[ARB_TILE], d.mu, d.eps, dt, f, df, A, alpha);
+  // every lane of the visit has read what it needs of A, P, aux: refill them (and the OTHER T buffer)
+  // for the warp's next contact visit while this one's sliding solves run
+  __syncwarp(vmask);
+  if (cn >= 0 && st.lane == (unsigned)(__ffs(vmask) - 1)) gs_stage_issue(st, b, cn, st.tsel ^ 1u);
+#if GS_STAGE_PF_F
+  // the forces of the next contact (written by this lane one sweep ago, read first thing in its visit):
+  // into the L1 by an asynchronous copy to the dump row (arb_prefetch_l1)
+  if (cn >= 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) arb_prefetch_l1(b.ff + (st.desc[cn].row + i) * ARB_TILE);
+  }
+#endif
+  if (br == 3) {
+    double newf[4];
+    softfinger_sliding(A, alpha, d.mu, d.eps, newf, status);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { df[i] = newf[i] - f[i]; f[i] = newf[i]; }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) pf[i * ARB_TILE] = f[i];
+  b.fbranch[c * ARB_TILE] = br;
+  double wv[6];
+  if (al) {
+    gs_aligned_wrench(sT, df, wv);
+#pragma unroll
+    for (int p = 0; p < 6; ++p) k.dy[p] += wv[p];
+  } else {
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+      double acc = 0.;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) acc += Tg[(i * 6 + p) * ARB_TILE] * df[i];
+      wv[p] = sign * acc;
+      k.dy[p] += wv[p];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    double acc = 0.;
+#pragma unroll
+    for (int p = 0; p < 6; ++p) acc += GSL(k, 6 * q + p) * wv[p];
+    k.u[q] += acc;
+  }
+  return br;
+}
+
+// fills the CTA's descriptor table (threads c < nc), the caller synchronises the CTA afterwards
+__device__ __forceinline__ void gs_desc_fill(const DevModel& m, GsDesc* desc, int c) {
+  GsDesc d;
+  d.type = m.ctype[c]; d.g1 = m.cgen1[c]; d.g0 = m.cgen0[c]; d.row = m.crow[c];
+  d.aligned = m.caligned[c];
+  d.gneed = -1; d.nneed = 0;
+  if (d.type == ARB_CONS_JOINT_LIMITS) { d.gneed = d.g1; d.nneed = 1; }
+  else if (!(d.g1 >= 0 && d.g0 >= 0)) { d.gneed = d.g1 < 0 ? d.g0 : d.g1; d.nneed = 6; }
+  // operands through the staging buffer: soft-finger contacts with one moving body
+  d.staged = d.type == ARB_CONS_SOFT_FINGER_PLANE_POINT && d.gneed >= 0;
+  const double* cd = m.cdbl + ARB_CONS_NDBL * c;
+  d.mu = cd[36]; d.eps[0] = cd[37]; d.eps[1] = cd[38]; d.eps[2] = cd[39];
+  desc[c] = d;
+}
+
+// All 32 lanes of the warp call this together (valid = false: a lane beyond the batch, given the view
+// of the last world and kept from writing); m.nc <= 32.
+__device__ unsigned long long world_fused_gs_staged(const DevModel& m, const DevBatch& b, int64_t w, bool valid, double dt,
+                                                    double* Lstore, int Lstride, GsStage& st) {
+  const unsigned FULL = 0xffffffffu;
+  const int NG = m.ngrows;
+  const int nc = m.nc;
+  int status = 0;
+  unsigned slid = 0u;
+  bool live = false;
+  if (valid) {
+    for (int c = 0; c < nc; ++c) live = live || FT(b.factive, c);
+    for (int g = 0; g < NG; ++g) FT(b.fy, g) = 0.;
+    if (live && gs_world_nonfinite(m, b)) {      // (see world_fused_gs)
+      b.status[w] |= ARB_STATUS_NONFINITE;
+      live = false;
+    }
+  }
+  const unsigned wlive = __ballot_sync(FULL, live);
+  if (wlive == 0u) return 0ull;
+  GsCache k;
+  k.g = -1;
+  k.n = 0;
+  k.L = Lstore;
+  k.ls = Lstride;
+  // amask: this world's active constraints; nmask: the visits it takes part in (its own, and the
+  // block switch at the head of a run of constraints in which it has an active one, see world_fused_gs)
+  unsigned amask = 0u, nmask = 0u;
+  if (live) {
+    for (int r = 0; r < m.nrows; ++r) FT(b.ff, r) = ST_LD(b.cforce, r);
+    gs_prologue(m, b, w, dt);
+    for (int c = 0; c < nc; ++c)
+      if (FT(b.factive, c)) amask |= 1u << c;
+    for (int c = 0; c < nc; ++c)
+      if ((amask & m.crunmask[c]) != 0u) nmask |= 1u << c;
+  }
+  unsigned smask = 0u;
+  for (int c = 0; c < nc; ++c)
+    if (st.desc[c].staged) smask |= 1u << c;
+  const unsigned wvis = __reduce_or_sync(FULL, nmask);              // the warp's schedule of a sweep
+  const unsigned wmask = __reduce_or_sync(FULL, amask) & smask;     // ... its staged contact visits
+  // the prologue wrote A_cc, pinv(A_cc), sdist/dt with ordinary stores: order them before the async proxy's reads
+  asm volatile("fence.proxy.async.global;" ::: "memory");
+  asm volatile("fence.proxy.async;" ::: "memory");
+  __syncwarp();
+  st.tsel = 0u;
+  if (wmask != 0u && st.lane == (unsigned)(__ffs(wlive) - 1)) gs_stage_issue(st, b, __ffs(wmask) - 1, 0u);
+  for (int sweep = 0; sweep < ARB_X_SWEEPS; ++sweep) {
+    for (unsigned mm = wvis; mm != 0u; mm &= mm - 1u) {
+      const int c = __ffs(mm) - 1;
+      const GsDesc& d = st.desc[c];
+      const bool act = ((amask >> c) & 1u) != 0u;
+      if (((nmask >> c) & 1u) != 0u && k.g != d.gneed) {
+#if GS_STAGE_SWITCH == 1
+        gs_cache_switch(m, b, w, k, d.gneed, d.nneed);
+#elif GS_STAGE_SWITCH == 2
+        // Lambda_GG is asked for before the flush (the old block's copy is dead by now): its round
+        // trip overlaps the flush's instead of following it
+        if (d.gneed >= 0) {
+          const double* pl = b.fLam + (d.gneed * NG + d.gneed) * ARB_TILE;
+          if (d.nneed == 6) {
+#pragma unroll
+            for (int p = 0; p < 6; ++p)
+#pragma unroll
+              for (int q = 0; q < 6; ++q) GSL(k, 6 * p + q) = pl[(p * NG + q) * ARB_TILE];
+          } else {
+            GSL(k, 0) = pl[0];
+          }
+        }
+        gs_cache_flush(m, b, w, k);
+        if (d.gneed >= 0) {
+          const double* pu = b.fu + d.gneed * ARB_TILE;
+          k.g = d.gneed;
+          k.n = d.nneed;
+#pragma unroll
+          for (int p = 0; p < 6; ++p) { k.dy[p] = 0.; k.u[p] = (p < d.nneed) ? pu[p * ARB_TILE] : 0.; }
+        }
+#else
+        gs_cache_flush(m, b, w, k);
+        if (d.gneed >= 0) gs_cache_load<true>(m, b, w, k, d.gneed, d.nneed);
+#endif
+      }
+      const unsigned vmask = __ballot_sync(FULL, act);
+      if (vmask == 0u) continue;
+      const bool staged = ((wmask >> c) & 1u) != 0u;
+      int cn = -1;      // the warp's next staged contact visit
+      if (staged) {
+        const unsigned hi = (wmask >> c) >> 1;
+        if (hi != 0u) cn = c + __ffs(hi);
+        else if (sweep + 1 < ARB_X_SWEEPS) cn = __ffs(wmask) - 1;
+      }
+      if (act) {
+        if (d.type == ARB_CONS_JOINT_LIMITS) {
+          gs_visit_limit(m, b, c, dt, k);
+        } else if (d.gneed < 0) {
+          gs_visit_two_body(m, b, w, c, dt, &status);
+        } else if (d.type == ARB_CONS_BALL_SOCKET) {
+          gs_visit_one_body<3>(m, b, w, c, dt, k, &status);
+        } else if (gs_visit_contact_staged(b, c, dt, k, &status, st, vmask, cn) == 3) {
+          slid |= 1u << c;
+        }
+      }
+      if (staged) { st.parity ^= 1u; st.tsel ^= 1u; }
+    }
+  }
+  if (!live) return 0ull;
+  gs_cache_flush(m, b, w, k);
+  gs_final_wrench(m, b);
+  for (int r = 0; r < m.nrows; ++r) ST(b.cforce, r) = FT(b.ff, r);
+  if (status) b.status[w] |= status;
+  return gs_sort_key(m, slid, amask);
+}
+#endif  // __CUDACC__
 
 // ---------------------------------------------------------------------------------------
 // Gauss-Seidel, block-cooperative form (the one the CUDA kernel runs).

@@ -28,6 +28,8 @@ struct arb_batch {
   int64_t launches = 0;
   int force_phases = 0;            // tests: run arb_step through the four phase kernels
   int gs_coop = 0;                 // 1: block-cooperative Gauss-Seidel kernel (pooled sliding solves) instead of the per-lane one
+  int gs_stage = 1;                // 1 (default): Gauss-Seidel kernel with the contact operands staged in shared memory by TMA
+                                   // (world_fused_gs_staged; models of at most 32 constraints), 0: operands loaded from global memory
   int time_stages = 0;             // 1: CUDA events around every fused stage (diagnostic, synchronises per step)
   double stage_ms[4] = {0., 0., 0., 0.};   // accumulated prepare / gs / finish milliseconds, [3] = steps timed
   FusedState* fused = nullptr;

@@ -142,6 +142,11 @@ int arb_batch_set_stream(arb_batch *batch, void *stream);
  *  "sort_period"  N: the fused step re-assigns the worlds to threads by contact state every N
  *                 steps (default 2; 0: never, worlds stay in arrival order); results are
  *                 bit-identical whatever the value;
+ *  "gs_stage"     1 (default): the Gauss-Seidel kernel finds the operands of a contact visit (the
+ *                 4x4 Delassus block, its pseudo-inverse, the contact map, sdist) in shared memory,
+ *                 copied there one visit ahead by TMA bulk copies (models of at most 32
+ *                 constraints; larger ones run the other kernel); 0: the kernel that loads them
+ *                 from global memory; bit-identical results;
  *  "gs_coop"      1: block-cooperative Gauss-Seidel kernel (sliding solves pooled through
  *                 shared memory) instead of the per-lane one; bit-identical results;
  *  "prepare_group" 1: the prepare stage runs with a group of 16 lanes per world and the world's

@@ -230,6 +230,32 @@ def test_cooperative_gauss_seidel_is_bit_identical_to_per_lane(torch_cuda):
     assert np.abs(out[0][2]).max() > 0        # contact forces are present
 
 
+def test_staged_gs_bit_identical(torch_cuda):
+    """The Gauss-Seidel kernel that stages A_cc and pinv(A_cc) of every contact visit in shared
+    memory (TMA bulk copies, option gs_stage) does the same arithmetic in the same order as the
+    kernel that loads them from global memory: states, forces, branches after 120 steps of falling
+    humanoids are equal bit for bit, for a batch that is not a multiple of the warp size, with and
+    without world sorting."""
+    from arboris_b200 import scenarios
+    from arboris_b200.flatten import flatten
+    model = flatten(scenarios.BUILDERS["human36_contact"]())
+    W = 1003
+    gpos, gvel = scenarios.initial_states(model, "human36_contact", 0, W)
+    out = []
+    for stage, sort in ((1, 2), (0, 2), (1, 0)):
+        bw = _batch(model, W)
+        bw.set_option("gs_stage", stage)
+        bw.set_option("sort_period", sort)
+        bw.set_state(gpos, gvel)
+        bw.step(1e-3, 120)
+        out.append(bw.get_state() + (bw.constraints("branch").cpu().numpy(), bw.status().cpu().numpy()))
+    for o in out[1:]:
+        for a, b in zip(out[0], o):
+            assert np.array_equal(a, b)
+    assert np.abs(out[0][2]).max() > 0        # contact forces are present
+    assert (out[0][3] == 3).any()             # some contact slides at the end
+
+
 # ---------------------------------------------------------------------------------------------
 # round 2: SURVEY.md 8(d) config 3 parity subset (64 worlds), free-running trajectories,
 # per-world controller parameters, body Jacobians on the GPU
