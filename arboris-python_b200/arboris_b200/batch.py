@@ -12,7 +12,6 @@ State tensors (fp64, device, world index fastest -- the layout the kernels
 coalesce on):  ``gpos`` (ngpos, W), ``gvel`` (ndof, W), ``cforce`` (nrows, W).
 """
 import ctypes as C
-import os
 
 import numpy as np
 import torch
@@ -370,9 +369,9 @@ class HostPipeline(object):
     (e.g. ``torch.empty(...).pin_memory().numpy()``), updated in place."""
 
     def __init__(self, world_or_model, nworlds, chunks="auto", device=None, mode="serial",
-                 compute_streams=3):
+                 compute_streams="priority"):
         """``chunks``: number of equal column blocks or their relative sizes (``shard.block_ranges``).
-        ``mode="serial"`` (default): the kernels of ALL blocks on ``compute_streams`` streams, block
+        ``mode="serial"`` (default): the kernels of ALL blocks on ``compute_streams`` streams (see below), block
         after block, the copies on two more streams ordered by events -- few kernels on the GPU at a
         time (kernels of different stages sharing an SM lose a fifth of their throughput once the
         worlds are sorted); with one compute stream every block and stage ends in a partial wave of
@@ -389,14 +388,19 @@ class HostPipeline(object):
         self.ranges = block_ranges(self.nworlds, chunks)
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         serial = mode == "serial"
-        ncs = max(1, int(compute_streams))
-        # ARB_B200_E2E_PRIO=1 (experiment): one compute stream per block, earlier blocks at higher
-        # priority, so that the blocks run nearly in order and a block's tail is filled by the next one
-        if serial and os.environ.get("ARB_B200_E2E_PRIO") == "1":
+        # compute streams of the serial mode: "priority" (default) = one stream per block, earlier blocks
+        # at higher priority, so that the blocks run nearly in order and the tail of a block's kernels
+        # is filled by the next block's (end to end +1.7 %, queued calls +4 % against three plain streams,
+        # profiles/README.md); an integer = that many plain streams, blocks assigned round robin
+        if serial and compute_streams == "priority":
             ncs = len(self.ranges)
-            self._css = [torch.cuda.Stream(dev, priority=max(-5, -(ncs - 1 - i))) for i in range(ncs)]
+            lo, hi = -5, 0            # (cudaDeviceGetStreamPriorityRange on B200: greatest -5, least 0)
+            self._css = [torch.cuda.Stream(dev, priority=max(lo, min(hi, -(ncs - 1 - i)))) for i in range(ncs)]
+        elif serial:
+            ncs = max(1, int(compute_streams))
+            self._css = [torch.cuda.Stream(dev) for _ in range(ncs)]
         else:
-            self._css = [torch.cuda.Stream(dev) for _ in range(ncs)] if serial else None
+            self._css = None
         self._hs = torch.cuda.Stream(dev) if serial else None            # host -> device copies
         self._ds = torch.cuda.Stream(dev) if serial else None            # device -> host copies
         first = BatchedWorld(world_or_model, self.ranges[0][1] - self.ranges[0][0], device=dev,
@@ -407,6 +411,7 @@ class HostPipeline(object):
                                              else torch.cuda.Stream(dev))
                                 for i, (w0, w1) in enumerate(self.ranges[1:])]
         self._ev = [(torch.cuda.Event(), torch.cuda.Event()) for _ in self.parts] if serial else None
+        self._ed = [torch.cuda.Event() for _ in self.parts] if serial else None     # copy-out of a block done
         torch.cuda.synchronize(dev)      # construction ran on the default stream
 
     @staticmethod
@@ -437,21 +442,38 @@ class HostPipeline(object):
             p._batch_h, g.ctypes.data, v.ctypes.data, cf, ld, 1 if to_device else 0,
             C.c_void_p(stream.cuda_stream)))
 
-    def _step_serial(self, gpos, gvel, cforce, dt, nsteps):
-        for (w0, w1), p, (eh, ec) in zip(self.ranges, self.parts, self._ev):
+    def _step_serial(self, gpos, gvel, cforce, dt, nsteps, sync=True):
+        for (w0, w1), p, (eh, ec), ed in zip(self.ranges, self.parts, self._ev, self._ed):
+            # (a block's copy-in waits for the copy-out of its previous call: the host arrays are
+            # updated in place, and calls may be queued without waiting, see step)
+            self._hs.wait_event(ed)
             self._copy(p, gpos, gvel, cforce, w0, w1, True, self._hs)
             eh.record(self._hs)
-        for (w0, w1), p, (eh, ec) in zip(self.ranges, self.parts, self._ev):
+        for (w0, w1), p, (eh, ec), ed in zip(self.ranges, self.parts, self._ev, self._ed):
             p._stream.wait_event(eh)
             p.step(dt, nsteps)
             ec.record(p._stream)
             self._ds.wait_event(ec)
             self._copy(p, gpos, gvel, cforce, w0, w1, False, self._ds)
-        self._ds.synchronize()
+            ed.record(self._ds)
+        if sync:
+            self._ds.synchronize()
 
-    def step(self, gpos, gvel, cforce, dt, nsteps=1):
+    def wait(self):
+        """Block until every queued call has delivered its results to the host arrays."""
         if self.mode == "serial":
-            return self._step_serial(gpos, gvel, cforce, dt, nsteps)
+            self._ds.synchronize()
+        else:
+            for p in self.parts:
+                p.synchronize()
+
+    def step(self, gpos, gvel, cforce, dt, nsteps=1, sync=True):
+        """Host arrays in, ``nsteps`` steps, host arrays out (in place).  ``sync=False`` (serial mode)
+        queues the call and returns: the next call's copies of a block start as soon as that block's
+        results of this call are on the host, while the later blocks of this call still compute --
+        no idle GPU between calls.  The host arrays must not be touched until ``wait()``."""
+        if self.mode == "serial":
+            return self._step_serial(gpos, gvel, cforce, dt, nsteps, sync)
         for (w0, w1), p in zip(self.ranges, self.parts):
             p.step_host_async(gpos[:, w0:w1], gvel[:, w0:w1],
                               cforce[:, w0:w1] if cforce is not None and cforce.size else None, dt, nsteps)

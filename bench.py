@@ -98,7 +98,9 @@ def parse():
     ap.add_argument("--e2e-mode", default="serial", choices=["serial", "streams"],
                     help="HostPipeline mode: 'serial' = the kernels of all blocks on --e2e-compute-streams "
                          "streams, block after block, copies on two more streams; 'streams' = one stream per block")
-    ap.add_argument("--e2e-compute-streams", type=int, default=3)
+    ap.add_argument("--e2e-compute-streams", type=lambda t: t if t == "priority" else int(t), default="priority",
+                    help="serial mode: 'priority' = one compute stream per block, earlier blocks at higher "
+                         "priority (default); N = N plain streams")
     ap.add_argument("--opt", action="append", help="arb_batch_set_option switch, name=value (A/B runs)")
     return ap.parse_args()
 
@@ -409,6 +411,23 @@ def measure(a, scen, model, w0, w1, rank, world_size, local, full):
             torch.cuda.synchronize()
             out["e2e"]["state_only_s_per_step"] = (time.perf_counter() - t0)/k2
             out["e2e"]["state_only_bytes"] = hgn.nbytes + hvn.nbytes
+        if pipe is not None and a.e2e_mode == "serial":
+            # the same pass with the calls QUEUED (HostPipeline.step(sync=False)): every step still moves
+            # its state host -> device and device -> host through the in-place host arrays (a block's
+            # copy-in waits for its own copy-out of the step before), but the host waits only when it
+            # touches the arrays (the episode restarts, every 25 steps) -- no idle GPU between steps
+            def host_steps_queued(c):
+                for _ in range(c):
+                    pipe.step(hgn, hvn, hfn if model.nrows else None, DT, 1, sync=False)
+                pipe.wait()
+            hep.step_fn = host_steps_queued
+            k3 = max(3, k_e2e//2)
+            hep.advance(3)
+            barrier()
+            t0 = time.perf_counter()
+            hep.advance(k3)
+            torch.cuda.synchronize()
+            out["e2e"]["queued_s_per_step"] = (time.perf_counter() - t0)/k3
         if pipe is not None:
             pipe.close()
         else:
@@ -423,11 +442,12 @@ def reduce_measure(m, device):
     """Max over ranks of the timed durations, sums of the counters."""
     from arboris_b200.shard import reduce_report
     e = m.get("e2e")
-    maxes = [m["ms"], e["s_per_step"]*1e3 if e else 0., e.get("state_only_s_per_step", 0.)*1e3 if e else 0.]
+    maxes = [m["ms"], e["s_per_step"]*1e3 if e else 0., e.get("state_only_s_per_step", 0.)*1e3 if e else 0.,
+             e.get("queued_s_per_step", 0.)*1e3 if e else 0.]
     sums = [m["nonfinite"], m["launches"], m["W"], m.get("flop_sum", 0.), m.get("active_sum", 0.),
             e["h2d"] if e else 0., e["d2h"] if e else 0.]
-    (ms_all, e2e_ms, e2e_state_ms), s = reduce_report(maxes, sums, device=device)
-    return {"ms": ms_all, "e2e_ms": e2e_ms, "e2e_state_ms": e2e_state_ms, "nonfinite": int(s[0]), "launches": int(s[1]),
+    (ms_all, e2e_ms, e2e_state_ms, e2e_queued_ms), s = reduce_report(maxes, sums, device=device)
+    return {"ms": ms_all, "e2e_ms": e2e_ms, "e2e_state_ms": e2e_state_ms, "e2e_queued_ms": e2e_queued_ms, "nonfinite": int(s[0]), "launches": int(s[1]),
             "worlds": int(s[2]), "flop_sum": s[3], "active_sum": s[4], "h2d": int(s[5]), "d2h": int(s[6])}
 
 
@@ -513,6 +533,7 @@ def run_ours(a):
     stage = {k: st[k]/nst for k in ("prepare", "gs", "finish")}
     tot_stage = sum(stage.values()) or 1.
     dom = max(stage, key=stage.get)
+    gs_unstaged = "gs_stage=0" in (a.opt or []) or model.nc > 32     # (arb_batch_set_option: gs_stage)
     dram_per_world = traffic.get("dram_bytes_per_world_step")
     exec_flop = traffic.get("executed_fp64_flop_per_world_step")
     out = {
@@ -547,7 +568,9 @@ def run_ours(a):
                                   % (head["active_sum"]/max(total_worlds, 1), int(model.nc)),
                      "per_launch": "one (prepare, gs, finish) triple = one step of the %d worlds of a GPU; "
                                    "achieved = worlds x flop_per_world_step / step time" % W,
-                     "stage_ms": stage, "dominant_kernel": "k_fused_" + dom,
+                     "stage_ms": stage,
+                     "dominant_kernel": {"prepare": "k_fused_prepare_lane", "finish": "k_fused_finish",
+                                         "gs": "k_fused_gs" if gs_unstaged else "k_fused_gs_staged"}[dom],
                      "dominant_share": stage[dom]/tot_stage,
                      "hbm": {"achieved": value/world_size*STATE_BYTES_PER_WORLD_STEP/1e9,
                              "peak": hbm_peak, "unit": "GB/s",
@@ -574,6 +597,13 @@ def run_ours(a):
                                "h2d_bytes_per_step": nb, "d2h_bytes_per_step": nb,
                                "how": "the same call with cforce = None: gpos and gvel travel, the constraint "
                                       "forces stay on the device"}
+        if r.get("e2e_queued_ms"):
+            o["queued"] = {"value": r["worlds"]/(r["e2e_queued_ms"]*1e-3), "unit": "world-steps/s",
+                           "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                           "how": "the same copies and steps with HostPipeline.step(sync=False): calls are "
+                                  "queued, a block's copy-in waits for its own copy-out of the step before, "
+                                  "the host waits (HostPipeline.wait) only before it touches the arrays "
+                                  "(episode restarts, every 25 steps)"}
         return o
     if "e2e" in m:
         out["e2e"] = e2e_obj(head)
@@ -585,9 +615,11 @@ def run_ours(a):
              "device -> host (gpos, gvel, cforce), all blocks synchronised, every step; same "
              "staggered episodes as the timed region"
              % (nblocks,
-                ("kernels of all blocks on %d streams, block after block, "
+                ("kernels of all blocks on %s, block after block, "
                  "arb_state_copy_host_strided copies on two more streams ordered by events"
-                 % a.e2e_compute_streams) if a.e2e_mode == "serial"
+                 % ("one stream per block, earlier blocks at higher priority"
+                    if a.e2e_compute_streams == "priority" else "%d streams" % a.e2e_compute_streams))
+                if a.e2e_mode == "serial"
                 else "arb_step_host_strided, one stream per block"))
             if nblocks > 1 else
             "arb_step_host: pinned host state -> device, 1 step, device -> host, "

@@ -104,7 +104,7 @@ def test_energy_monitor_matches_mass_matrix():
     assert np.abs(e[-1] - e[0]).max() < 2e-2*np.abs(e[0]).max()      # semi-implicit Euler, dt = 1 ms
 
 
-@pytest.mark.parametrize("mode", ["streams", "serial"])
+@pytest.mark.parametrize("mode", ["streams", "serial", "serial-queued"])
 def test_host_pipeline_equals_device_step(mode):
     """HostPipeline (column blocks of pinned host state; one stream each with arb_step_host_strided,
     or all kernels on one stream and the copies of arb_state_copy_host_strided on two others)
@@ -120,9 +120,11 @@ def test_host_pipeline_equals_device_step(mode):
     hg = torch.as_tensor(gp).pin_memory()
     hv = torch.as_tensor(gv).pin_memory()
     hf = torch.zeros((model.nrows, W), dtype=torch.float64).pin_memory()
-    pipe = HostPipeline(model, W, chunks=7, device="cuda:0", mode=mode)
+    pipe = HostPipeline(model, W, chunks=7, device="cuda:0", mode=mode.split("-")[0])
     for _ in range(90):
-        pipe.step(hg.numpy(), hv.numpy(), hf.numpy(), 1e-3, 1)
+        # ("serial-queued": calls queued without waiting, HostPipeline.wait at the end)
+        pipe.step(hg.numpy(), hv.numpy(), hf.numpy(), 1e-3, 1, sync=not mode.endswith("queued"))
+    pipe.wait()
     bw.step(1e-3, 90)
     g, v, f = bw.get_state()
     assert np.array_equal(g, hg.numpy()) and np.array_equal(v, hv.numpy()) and np.array_equal(f, hf.numpy())
