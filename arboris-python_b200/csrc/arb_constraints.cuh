@@ -185,12 +185,13 @@ ARB_NOINLINE void softfinger_sliding_lu(const double* A, const double* alpha, do
 // Sliding branch of SoftFingerContact.solve (constraints.py:803-836): s = smallest real
 // eigenvalue <= 0 of B (with the reference's scalar inner products), then
 // newf = (A - s diag(eps^-2, 0))^-1 (-alpha).
+// coop: see sliding_root_structured (the lanes of the warp that make this call together; 0: unknown)
 ARB_NOINLINE void softfinger_sliding(const double* A, const double* alpha, double mu, const double* eps,
-                              double* newf, int* status) {
+                              double* newf, int* status, unsigned coop = 0u) {
   double s = 0.;
   bool found = false;
   const bool unit_eps = (eps[0] == 1. && eps[1] == 1. && eps[2] == 1.);
-  if (!(unit_eps && sliding_root_structured(A, alpha, mu, &s, &found))) {
+  if (!(unit_eps && sliding_root_structured(A, alpha, mu, &s, &found, coop))) {
     const double Yc[3] = {A[3], A[7], A[11]};
     const double yn = A[15];
     double beta[3], bb[3];

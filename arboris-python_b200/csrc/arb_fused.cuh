@@ -1058,6 +1058,12 @@ ARB_D unsigned long long world_fused_gs(const DevModel& m, const DevBatch& b, in
 #ifndef GS_STAGE_PF_F
 #define GS_STAGE_PF_F 0
 #endif
+#ifndef GS_STAGE_COOP_ROOT
+#define GS_STAGE_COOP_ROOT 1  /* the sliding lanes of a visit are balloted before the solve and enter it together, the mask goes
+                                 down to sliding_root_structured (which then has no early exits, and can share the
+                                 sampling search of ARB_SAMPLE_ROOT): gs 7.15 -> 6.93 ms at 262144 worlds, 1.85 -> 1.73 at
+                                 32768 with the ballot alone (profiles/ab_r04/r04o_*; 0: A/B builds) */
+#endif
 #ifndef GS_STAGE_SWITCH
 #define GS_STAGE_SWITCH 0     /* 0: flush, then load; 1: one round trip (gs_cache_switch); 2: Lambda_GG requested before the flush (A/B builds) */
 #endif
@@ -1205,9 +1211,14 @@ __device__ __forceinline__ int gs_visit_contact_staged(const DevBatch& b, int c,
     for (int i = 0; i < 4; ++i) arb_prefetch_l1(b.ff + (st.desc[cn].row + i) * ARB_TILE);
   }
 #endif
+#if GS_STAGE_COOP_ROOT
+  const unsigned slmask = __ballot_sync(vmask, br == 3);      // the lanes that solve a sliding problem now
+#else
+  const unsigned slmask = 0u;
+#endif
   if (br == 3) {
     double newf[4];
-    softfinger_sliding(A, alpha, d.mu, d.eps, newf, status);
+    softfinger_sliding(A, alpha, d.mu, d.eps, newf, status, slmask);
 #pragma unroll
     for (int i = 0; i < 4; ++i) { df[i] = newf[i] - f[i]; f[i] = newf[i]; }
   }

@@ -460,9 +460,109 @@ static long arb_fastroot_fail[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // ... and why it
 #else
 #define ARB_FAIL(i) 0
 #endif
+// Certificate, valid whatever the roots are: if the Taylor coefficients 1..5 of the monic sextic p at x
+// are positive (repeated synthetic division), p' > 0 on (x, inf): a root x is then the largest real root.
+ARB_HD bool poly6_certify(const double* p, double x) {
+  double b[7];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) b[k] = p[k];
+  b[6] = 1.;
+#pragma unroll
+  for (int j = 0; j < 6; ++j)
+#pragma unroll
+    for (int k = 5; k >= j; --k) b[k] += x * b[k + 1];
+  bool pos = true;
+#pragma unroll
+  for (int k = 1; k < 6; ++k) pos = pos && (b[k] > 0.);
+  return pos;
+}
+// Sampling search of the largest root in [0, T] of a sextic that left the fast path (not real-rooted:
+// the start bound sits where p' <= 0, or the variance of the roots is negative; 1 % of the sliding
+// solves).  Each round evaluates p at 32 equidistant points of the bracket; the rightmost sample with
+// p <= 0 gives the next bracket (p > 0 at its right end), 33 times narrower: four rounds to 1e-6 T.  A pair
+// of roots between two samples is missed, so the result is only a candidate: the caller refines it
+// (poly_refine) and runs poly6_certify; what fails the certificate goes to the rigorous isolation as
+// before.  coop != 0 (device): the lanes of coop -- all of them here, with the same q: the sliding lanes
+// of one contact visit helping ONE of them -- share the 32 samples of a round; coop == 0: the calling
+// lane evaluates them itself.  Same sample points, same Horner evaluations, same decisions either way:
+// the result does not depend on who computes it (bit-identical kernels and batch compositions).
+// ~10 instructions per round and lane with a full warp where the isolation costs a few thousand.
+// MEASURED SLOWER (ARB_SAMPLE_ROOT = 0 is the default): only a third of the polynomials that reach this
+// point pass the certificate afterwards (host counters: 2 087 of 6 267) -- where p' <= 0 somewhere right
+// of the largest root the Taylor coefficients there cannot all be positive -- so two thirds pay the search
+// AND the isolation: gs 7.59 ms against 6.93 at 262 144 worlds, 1.92 against 1.82 at 32 768
+// (profiles/ab_r04/r04n_*).  A certificate that admits those roots would have to bound p from below
+// between the root and the Cauchy bound.
+// Returns 1: bracket (lo, hi) with p(lo) <= 0 < p(hi); 0: p > 0 at every sample (no candidate).
+ARB_HD int poly6_sample_bracket(const double* q, unsigned coop, double* lo_out, double* hi_out) {
+  double T = 0.;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) T = fmax(T, fabs(q[k]));
+  T += 1.;
+  if (!(T < 1e300)) return 0;
+#ifdef __CUDA_ARCH__
+  const unsigned lane = threadIdx.x & 31u;
+  const int n = coop ? __popc(coop) : 1, rank = coop ? __popc(coop & ((1u << lane) - 1u)) : 0;
+#endif
+  double lo = 0., hi = T;
+  bool have = !(q[0] > 0.);          // p(0) <= 0: (0, T) holds a root
+  for (int round = 0; round < 16; ++round) {
+    const double h = (hi - lo) * (1. / 33.);
+    int jbest = -1;                   // the rightmost sample x_j = lo + h (j + 1), j = 0..31, with p <= 0
+#ifdef __CUDA_ARCH__
+    if (coop != 0u) {
+      for (int j = rank; j < 32; j += n) {
+        const double x = lo + h * (double)(j + 1);
+        double f = 1.;
+#pragma unroll
+        for (int k = 5; k >= 0; --k) f = f * x + q[k];
+        if (!(f > 0.)) jbest = j;
+      }
+      jbest = __reduce_max_sync(coop, jbest);
+    } else
+#endif
+    {
+      for (int j = 31; j >= 0; --j) {
+        const double x = lo + h * (double)(j + 1);
+        double f = 1.;
+#pragma unroll
+        for (int k = 5; k >= 0; --k) f = f * x + q[k];
+        if (!(f > 0.)) { jbest = j; break; }
+      }
+    }
+    if (jbest >= 0) {
+      const double nlo = lo + h * (double)(jbest + 1);
+      hi = (jbest + 1 < 32) ? lo + h * (double)(jbest + 2) : hi;
+      lo = nlo;
+      have = true;
+    } else if (have) {
+      hi = lo + h;                    // p(lo) <= 0 < p(lo + h)
+    } else {
+      return 0;
+    }
+    if (!(hi - lo > 1e-6 * T)) break;
+  }
+  *lo_out = lo;
+  *hi_out = hi;
+  return 1;
+}
 // root of the sextic in a bracket the failed fast iteration already holds (out of line: rare lanes)
 ARB_NOINLINE double poly6_refine_bracket(const double* p, double lo, double hi, double flo) {
   return poly_refine<6>(p, lo, hi, flo);
+}
+// candidate of poly6_sample_bracket -> certified largest root (1), "no root t >= 0" as t = -1 (1), or 0
+ARB_HD int poly6_from_samples(const double* p, int got, double lo, double hi, double* t) {
+  if (got) {
+    const double flo = poly_val<6>(p, lo);
+    const double tc = (flo == 0.) ? lo : poly6_refine_bracket(p, lo, hi, flo);
+    if (poly6_certify(p, tc)) { *t = tc; return 1; }
+    return 0;
+  }
+  if (p[0] > 0. && p[1] > 0. && p[2] > 0. && p[3] > 0. && p[4] > 0. && p[5] > 0.) {
+    *t = -1.;       // all coefficients positive: no root t >= 0
+    return 1;
+  }
+  return 0;
 }
 #ifndef ARB_FASTROOT_RECOVER
 #define ARB_FASTROOT_RECOVER 1   /* cheap recoveries of the fast path before the rigorous isolation (0: A/B builds) */
@@ -560,19 +660,7 @@ ARB_HD int poly6_largest_root_fast(const double* p, double* root) {
     x = xn;
   }
   if (!conv) return ARB_FAIL(3);
-  // Taylor coefficients of p at x (repeated synthetic division), b[1..5] must be > 0
-  double b[7];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) b[k] = p[k];
-  b[6] = 1.;
-#pragma unroll
-  for (int j = 0; j < 6; ++j)
-#pragma unroll
-    for (int k = 5; k >= j; --k) b[k] += x * b[k + 1];
-  bool pos = true;
-#pragma unroll
-  for (int k = 1; k < 6; ++k) pos = pos && (b[k] > 0.);
-  if (!pos) return ARB_FAIL(4);
+  if (!poly6_certify(p, x)) return ARB_FAIL(4);
   *root = x;
 #ifdef ARB_HOSTTEST_COUNTERS
   ++arb_fastroot_hits;
@@ -580,13 +668,20 @@ ARB_HD int poly6_largest_root_fast(const double* p, double* root) {
   return 1;
 }
 
+#ifndef ARB_SAMPLE_ROOT
+#define ARB_SAMPLE_ROOT 0     /* 1: sampling search (poly6_sample_bracket) before the rigorous isolation -- measured slower, see there */
+#endif
 #ifndef ARB_POLISH_ITERS
 #define ARB_POLISH_ITERS 1   /* one Newton step on det M(t) brings the root of the expanded sextic to ~1e-14 of LAPACK's */
 #endif
 // A: 4x4 contact admittance block, alpha: the vector of constraints.py:807-808, mu: friction.
 // Returns false if the structured path does not apply (caller falls back to the general
 // eigenvalue routine); else *found tells whether a real eigenvalue <= 0 exists and *s_out is it.
-ARB_HD bool sliding_root_structured(const double* A, const double* alpha, double mu, double* s_out, bool* found) {
+// coop (device): the lanes of the warp that are in this call together (0: none known) -- they help the
+// lanes whose polynomial leaves the fast path (poly6_coop_bracket); every lane of coop must get here,
+// so nothing returns before that point.
+ARB_HD bool sliding_root_structured(const double* A, const double* alpha, double mu, double* s_out, bool* found,
+                                    unsigned coop = 0u) {
   const double Yc[3] = {A[3], A[7], A[11]};
   const double yn = A[15];
   // one reciprocal of y_n and one of a instead of five divisions (the reference divides: mu/y_n*alpha_n
@@ -630,7 +725,8 @@ ARB_HD bool sliding_root_structured(const double* A, const double* alpha, double
       sigma = fmax(sigma, fabs(Q[3 * i + j]) + fabs(cc));
     }
 #endif
-  if (!(sigma > 0.) || !(sigma < 1e300)) return false;
+  bool bad = !(sigma > 0.) || !(sigma < 1e300);
+  if (bad && coop == 0u) return false;
   // scaled coefficients of  M(t) = t^2 I + t C1 + C0,  s = -sigma t
   const double is = 1. / sigma;
   double C1[9], C0[9];
@@ -668,10 +764,39 @@ ARB_HD bool sliding_root_structured(const double* A, const double* alpha, double
     }
 #undef ARB_QUAD
   }
-  if (!(fabs(p[6] - 1.) < 1e-9)) return false;
+  bad = bad || !(fabs(p[6] - 1.) < 1e-9);
+  if (bad && coop == 0u) return false;
   p[6] = 1.;
-  double t;
-  if (poly6_largest_root_fast(p, &t)) {
+  double t = 0.;
+  int ok = bad ? 0 : poly6_largest_root_fast(p, &t);
+#if ARB_SAMPLE_ROOT
+#ifdef __CUDA_ARCH__
+  if (coop != 0u) {
+    unsigned fm = __ballot_sync(coop, !bad && !ok);
+    while (fm != 0u) {
+      const int src = __ffs(fm) - 1;
+      fm &= fm - 1u;
+      double q[6], lo = 0., hi = 0.;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) q[k] = __shfl_sync(coop, p[k], src);
+      const int got = poly6_sample_bracket(q, coop, &lo, &hi);
+      if ((int)(threadIdx.x & 31u) == src) ok = poly6_from_samples(p, got, lo, hi, &t);
+    }
+    if (bad) return false;
+  } else
+#endif
+  if (!ok) {
+    double lo = 0., hi = 0.;
+    const int got = poly6_sample_bracket(p, 0u, &lo, &hi);
+    ok = poly6_from_samples(p, got, lo, hi, &t);
+#ifdef ARB_HOSTTEST_COUNTERS
+    if (ok) { ++arb_fastroot_fail[6]; }
+#endif
+  }
+#else
+  if (bad) return false;
+#endif
+  if (ok) {
     if (t < 0.) { *found = false; *s_out = 0.; return true; }   // every real eigenvalue is > 0
   } else {
     // (Cauchy bound of the roots, needed by the rigorous isolation only: the fast path rejects
