@@ -111,6 +111,7 @@ __global__ void __launch_bounds__(THREADS, GS_MINBLOCKS) k_fused_gs_staged(DevMo
   __shared__ __align__(128) double sbuf[(THREADS / 32) * (GS_STAGE_WARP_BYTES / 8)];
   __shared__ __align__(16) GsDesc sdesc[32];
   __shared__ __align__(8) unsigned long long sbar[THREADS / 32];
+  __shared__ const double* swbase[THREADS / 32][5];
   const unsigned lane = threadIdx.x & 31u, wp = threadIdx.x >> 5;
   GsStage st;
   st.buf = sbuf + wp * (GS_STAGE_WARP_BYTES / 8);
@@ -120,9 +121,15 @@ __global__ void __launch_bounds__(THREADS, GS_MINBLOCKS) k_fused_gs_staged(DevMo
   st.tsel = 0u;
   st.lane = lane;
   st.desc = sdesc;
+  st.wbase = swbase[wp];
   if (lane == 0u) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st.bar_s) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const int64_t s0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // the first slot of the warp's tile
+    if (s0 < b.W) {
+      const DevBatch t = fused_tile_view(b, s0);
+      swbase[wp][0] = t.fAcc; swbase[wp][1] = t.fP; swbase[wp][2] = t.faux; swbase[wp][3] = t.fT1; swbase[wp][4] = t.fT0;
+    }
   }
   if ((int)threadIdx.x < m.nc) gs_desc_fill(m, sdesc, threadIdx.x);
   __syncthreads();

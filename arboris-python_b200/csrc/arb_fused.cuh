@@ -1084,24 +1084,26 @@ struct GsStage {
   unsigned tsel;        // which T buffer the CURRENT visit reads (warp-uniform)
   unsigned lane;
   const GsDesc* desc;   // [nc] in shared memory
+  const double* const* wbase;   // [5] in shared memory: lane 0's pointers into the warp's tile (fAcc, fP, faux, fT1, fT0)
 };
 __device__ __forceinline__ void gs_bulk_g2s(unsigned dst_s, const double* src, unsigned bytes, unsigned bar_s) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst_s), "l"(src), "r"(bytes), "r"(bar_s) : "memory");
 }
-// refill for constraint c; tnext: the T buffer the visit of c will read
-__device__ __forceinline__ void gs_stage_issue(const GsStage& st, const DevBatch& b, int c, unsigned tnext) {
-  // b is the issuing lane's view of its tile: lane 0's element is st.lane doubles below
+// refill for constraint c; tnext: the T buffer the visit of c will read.  One lane issues; the source
+// addresses come from the warp's tile pointers in shared memory (assembling them from the lane's own
+// view -- spilled 64-bit pointers minus the lane index -- was 95 instructions per visit, 7 % of the kernel's)
+__device__ __forceinline__ void gs_stage_issue(const GsStage& st, int c, unsigned tnext) {
   const GsDesc& d = st.desc[c];
   const unsigned tb = d.aligned ? (unsigned)GS_STAGE_T_BYTES : 0u;
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
                ::"r"(st.bar_s), "r"((unsigned)(GS_STAGE_AP_BYTES + GS_STAGE_AUX_BYTES) + tb) : "memory");
-  gs_bulk_g2s(st.buf_s, b.fAcc + d.row * (4 * ARB_TILE) - st.lane, 16 * ARB_TILE * 8, st.bar_s);
-  gs_bulk_g2s(st.buf_s + 16 * ARB_TILE * 8, b.fP + d.row * (4 * ARB_TILE) - st.lane, 16 * ARB_TILE * 8, st.bar_s);
-  gs_bulk_g2s(st.buf_s + GS_STAGE_AP_BYTES, b.faux + c * (4 * ARB_TILE) - st.lane, GS_STAGE_AUX_BYTES, st.bar_s);
+  gs_bulk_g2s(st.buf_s, st.wbase[0] + d.row * (4 * ARB_TILE), 16 * ARB_TILE * 8, st.bar_s);
+  gs_bulk_g2s(st.buf_s + 16 * ARB_TILE * 8, st.wbase[1] + d.row * (4 * ARB_TILE), 16 * ARB_TILE * 8, st.bar_s);
+  gs_bulk_g2s(st.buf_s + GS_STAGE_AP_BYTES, st.wbase[2] + c * (4 * ARB_TILE), GS_STAGE_AUX_BYTES, st.bar_s);
   if (d.aligned)
     gs_bulk_g2s(st.buf_s + GS_STAGE_AP_BYTES + GS_STAGE_AUX_BYTES + tnext * GS_STAGE_T_BYTES,
-                (d.g1 < 0 ? b.fT0 : b.fT1) + c * (24 * ARB_TILE) - st.lane, GS_STAGE_T_BYTES, st.bar_s);
+                st.wbase[d.g1 < 0 ? 4 : 3] + c * (24 * ARB_TILE), GS_STAGE_T_BYTES, st.bar_s);
 }
 __device__ __forceinline__ void gs_stage_wait(const GsStage& st) {
   asm volatile(
@@ -1202,7 +1204,7 @@ __device__ __forceinline__ int gs_visit_contact_staged(const DevBatch& b, int c,
   // every lane of the visit has read what it needs of A, P, aux: refill them (and the OTHER T buffer)
   // for the warp's next contact visit while this one's sliding solves run
   __syncwarp(vmask);
-  if (cn >= 0 && st.lane == (unsigned)(__ffs(vmask) - 1)) gs_stage_issue(st, b, cn, st.tsel ^ 1u);
+  if (cn >= 0 && st.lane == (unsigned)(__ffs(vmask) - 1)) gs_stage_issue(st, cn, st.tsel ^ 1u);
 #if GS_STAGE_PF_F
   // the forces of the next contact (written by this lane one sweep ago, read first thing in its visit):
   // into the L1 by an asynchronous copy to the dump row (arb_prefetch_l1)
@@ -1311,7 +1313,7 @@ __device__ unsigned long long world_fused_gs_staged(const DevModel& m, const Dev
   asm volatile("fence.proxy.async;" ::: "memory");
   __syncwarp();
   st.tsel = 0u;
-  if (wmask != 0u && st.lane == (unsigned)(__ffs(wlive) - 1)) gs_stage_issue(st, b, __ffs(wmask) - 1, 0u);
+  if (wmask != 0u && st.lane == (unsigned)(__ffs(wlive) - 1)) gs_stage_issue(st, __ffs(wmask) - 1, 0u);
   for (int sweep = 0; sweep < ARB_X_SWEEPS; ++sweep) {
     for (unsigned mm = wvis; mm != 0u; mm &= mm - 1u) {
       const int c = __ffs(mm) - 1;
