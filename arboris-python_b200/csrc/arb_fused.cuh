@@ -1064,6 +1064,9 @@ ARB_D unsigned long long world_fused_gs(const DevModel& m, const DevBatch& b, in
                                  sampling search of ARB_SAMPLE_ROOT): gs 7.15 -> 6.93 ms at 262144 worlds, 1.85 -> 1.73 at
                                  32768 with the ballot alone (profiles/ab_r04/r04o_*; 0: A/B builds) */
 #endif
+#ifndef GS_STAGE_PF_SWITCH
+#define GS_STAGE_PF_SWITCH 0  /* 1: the rows of an upcoming block switch's flush prefetched into the L1 (A/B builds) */
+#endif
 #ifndef GS_STAGE_SWITCH
 #define GS_STAGE_SWITCH 0     /* 0: flush, then load; 1: one round trip (gs_cache_switch); 2: Lambda_GG requested before the flush (A/B builds) */
 #endif
@@ -1359,6 +1362,27 @@ __device__ unsigned long long world_fused_gs_staged(const DevModel& m, const Dev
         else if (sweep + 1 < ARB_X_SWEEPS) cn = __ffs(wmask) - 1;
       }
       if (act) {
+#if GS_STAGE_PF_SWITCH
+        {   // a block switch follows this visit: ask for the rows its flush will read (true L1 prefetch)
+          const unsigned rest = (wvis >> c) >> 1;
+          const int c2 = rest != 0u ? c + __ffs(rest) : __ffs(wvis) - 1;
+          if (st.desc[c2].gneed != d.gneed && k.g >= 0) {
+            const int nout = NG - k.n;
+            const double* pl = b.fLam + k.g * ARB_TILE;
+#pragma unroll 1
+            for (int i = 0; i < nout; ++i) {
+              const int r = i < k.g ? i : i + k.n;
+              const double* q = pl + r * (NG * ARB_TILE);
+              if (k.n == 6) {
+#pragma unroll
+                for (int p = 0; p < 6; ++p) arb_prefetch_l1(q + p * ARB_TILE);
+              } else {
+                arb_prefetch_l1(q);
+              }
+            }
+          }
+        }
+#endif
         if (d.type == ARB_CONS_JOINT_LIMITS) {
           gs_visit_limit(m, b, c, dt, k);
         } else if (d.gneed < 0) {
