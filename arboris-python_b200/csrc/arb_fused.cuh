@@ -875,11 +875,36 @@ ARB_NOINLINE void gs_prologue(const DevModel& m, const DevBatch& b, int64_t w, d
 }
 
 // JointLimits.solve (constraints.py:73-90) on the cached 1-row block
+// JointLimits visit (constraints.py:35-90).  The generator row of a limited dof is NOT cached: whatever
+// block the sweep holds stays where it is.  The row's velocity is its memory copy plus what the cached
+// block's pending wrench would add at its flush, u_g = u[g] + Lambda[g, F] dy_F (6 loads), and the
+// force increment goes straight into u: the rows of the cached block in registers, the others in memory
+// (u[r] += Lambda[r, g] df).  Round 2 cached the row as a 1-row block, which made every limit two block
+// switches (flush the body's block: 8 rows x 6 loads + stores, load the row, flush it again: 13 rows,
+// reload the body's block: 42 loads) -- four switches per sweep for human36's two feet and two knees
+// where two are needed, each a chain of three memory round trips.
 ARB_D void gs_visit_limit(const DevModel& m, const DevBatch& b, int c, double dt, GsCache& k) {
+  const int NG = m.ngrows;
   const double* cd = m.cdbl + ARB_CONS_NDBL * c;
   const int r0 = m.crow[c];
+  const int g = m.cgen1[c];
+  const int rowstride = NG * ARB_TILE;
   const double a = FT(b.fAcc, r0 * 4), p = FT(b.fP, r0 * 4);
-  const double f = FT(b.ff, r0), v = k.u[0], q = FT(b.faux, 4 * c);
+  const double f = FT(b.ff, r0), q = FT(b.faux, 4 * c);
+  double v = FT(b.fu, g);
+  if (k.g >= 0) {
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) any = any || (i < k.n && k.dy[i] != 0.);
+    if (any) {
+      const double* pl = b.fLam + (g * NG + k.g) * ARB_TILE;
+      double acc = 0.;
+#pragma unroll
+      for (int i = 0; i < 6; ++i)
+        if (i < k.n) acc += pl[i * ARB_TILE] * k.dy[i];
+      v = v + acc;
+    }
+  }
   const double pred = q + dt * (v - a * f);
   double nf;
   int br;
@@ -890,8 +915,27 @@ ARB_D void gs_visit_limit(const DevModel& m, const DevBatch& b, int c, double dt
   FT(b.ff, r0) = nf;
   FT(b.fbranch, c) = br;
   if (df != 0.) {
-    k.dy[0] += df;
-    k.u[0] += GSL(k, 0) * df;
+    const double* col = b.fLam + g * ARB_TILE;          // Lambda[r, g] = col[r rowstride]
+    const int kg = k.g, kn = k.g >= 0 ? k.n : 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+      if (i < kn) k.u[i] += col[(kg + i) * rowstride] * df;
+    const int nout = NG - kn;
+#pragma unroll 1
+    for (int i0 = 0; i0 < nout; i0 += 4) {
+      double lam[4], uu[4];
+      int rr[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ii = i0 + i < nout ? i0 + i : nout - 1;
+        rr[i] = (kn > 0 && ii >= kg) ? ii + kn : ii;
+        lam[i] = col[rr[i] * rowstride];
+        uu[i] = b.fu[rr[i] * ARB_TILE];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i0 + i < nout) b.fu[rr[i] * ARB_TILE] = uu[i] + lam[i] * df;
+    }
   }
 }
 
@@ -1008,9 +1052,9 @@ ARB_D unsigned long long world_fused_gs(const DevModel& m, const DevBatch& b, in
     // the block this visit needs in the cache: a limited dof (1 row), the moving body of a
     // one-body constraint (6 rows), or none (two-body constraints go through memory; the end)
     int gneed = -1, nneed = 0;
-    if (type == ARB_CONS_JOINT_LIMITS) { gneed = g1; nneed = 1; }
-    else if (!last && !(g1 >= 0 && g0 >= 0)) { gneed = g1 < 0 ? g0 : g1; nneed = 6; }
-    if (k.g != gneed) {
+    const bool keep = type == ARB_CONS_JOINT_LIMITS;      // a limit visit works with whatever block is cached
+    if (!last && !keep && !(g1 >= 0 && g0 >= 0)) { gneed = g1 < 0 ? g0 : g1; nneed = 6; }
+    if (!keep && k.g != gneed) {
       gs_cache_flush(m, b, w, k);
       if (gneed >= 0) gs_cache_load<true>(m, b, w, k, gneed, nneed);
     }
@@ -1261,7 +1305,7 @@ __device__ __forceinline__ void gs_desc_fill(const DevModel& m, GsDesc* desc, in
   d.type = m.ctype[c]; d.g1 = m.cgen1[c]; d.g0 = m.cgen0[c]; d.row = m.crow[c];
   d.aligned = m.caligned[c];
   d.gneed = -1; d.nneed = 0;
-  if (d.type == ARB_CONS_JOINT_LIMITS) { d.gneed = d.g1; d.nneed = 1; }
+  if (d.type == ARB_CONS_JOINT_LIMITS) { d.gneed = -2; }      // (-2: keeps whatever block is cached)
   else if (!(d.g1 >= 0 && d.g0 >= 0)) { d.gneed = d.g1 < 0 ? d.g0 : d.g1; d.nneed = 6; }
   // operands through the staging buffer: soft-finger contacts with one moving body
   d.staged = d.type == ARB_CONS_SOFT_FINGER_PLANE_POINT && d.gneed >= 0;
@@ -1322,7 +1366,7 @@ __device__ unsigned long long world_fused_gs_staged(const DevModel& m, const Dev
       const int c = __ffs(mm) - 1;
       const GsDesc& d = st.desc[c];
       const bool act = ((amask >> c) & 1u) != 0u;
-      if (((nmask >> c) & 1u) != 0u && k.g != d.gneed) {
+      if (((nmask >> c) & 1u) != 0u && d.gneed != -2 && k.g != d.gneed) {
 #if GS_STAGE_SWITCH == 1
         gs_cache_switch(m, b, w, k, d.gneed, d.nneed);
 #elif GS_STAGE_SWITCH == 2
@@ -1643,10 +1687,6 @@ ARB_D unsigned long long world_fused_gs_coop(const DevModel& m, const DevBatch& 
       // block switches per world and per run of constraints, as in world_fused_gs
       const bool needs = c < 32 ? (amask & (unsigned long long)m.crunmask[c]) != 0ull : act;
       if (type == ARB_CONS_JOINT_LIMITS) {
-        if (needs && k.g != g1) {
-          gs_cache_flush(m, b, w, k);
-          gs_cache_load<true>(m, b, w, k, g1, 1);
-        }
         if (act) gs_visit_limit(m, b, c, dt, k);
         continue;
       }

@@ -210,21 +210,27 @@ static inline int build_host_model(const arb_model_desc* d, HostModel& m, std::s
   m.doflim.assign(m.ndof > 0 ? m.ndof : 1, 0);
   for (size_t i = 0; i < m.glimdof.size(); ++i) m.doflim[m.glimdof[i]] = 1;
   // Runs of the Gauss-Seidel sweep: consecutive constraints that work on the same cached generator
-  // block (the moving body of a one-body constraint, or a limited dof).  A world switches to the
-  // block at the first constraint of the run iff one of ITS constraints in the run is active.
+  // block (the moving body of a one-body constraint).  A world switches to the block at the first
+  // constraint of the run iff one of ITS constraints in the run is active.  Joint limits work with
+  // whatever block is cached (gs_visit_limit): they neither form nor break a run.
   {
     m.crunmask.assign(m.nc > 0 ? m.nc : 1, 0u);
     auto block_of = [&](int c) {
-      if (m.ctype[c] == ARB_CONS_JOINT_LIMITS) return m.cgen1[c];
       if (m.cgen1[c] >= 0 && m.cgen0[c] >= 0) return -1 - c;      // two-body constraint: no cached block, its own run
       return m.cgen1[c] < 0 ? m.cgen0[c] : m.cgen1[c];
     };
-    for (int c = 0; c < m.nc && c < 32; ) {
+    const int nb = m.nc < 32 ? m.nc : 32;
+    for (int c = 0; c < nb; ) {
+      if (m.ctype[c] == ARB_CONS_JOINT_LIMITS) { m.crunmask[c] = 1u << c; ++c; continue; }
+      unsigned mask = 1u << c;
       int e = c + 1;
-      while (e < m.nc && e < 32 && block_of(e) == block_of(c)) ++e;
-      unsigned mask = 0u;
-      for (int i = c; i < e; ++i) mask |= 1u << i;
-      for (int i = c; i < e; ++i) m.crunmask[i] = mask;
+      while (e < nb && (m.ctype[e] == ARB_CONS_JOINT_LIMITS || block_of(e) == block_of(c))) {
+        if (m.ctype[e] != ARB_CONS_JOINT_LIMITS) mask |= 1u << e;
+        ++e;
+      }
+      while (e > c + 1 && m.ctype[e - 1] == ARB_CONS_JOINT_LIMITS) --e;    // trailing limits belong to no run
+      for (int i = c; i < e; ++i)
+        m.crunmask[i] = (m.ctype[i] == ARB_CONS_JOINT_LIMITS) ? (1u << i) : mask;
       c = e;
     }
   }
