@@ -301,12 +301,14 @@ struct GsCache {
 };
 #define GSL(k, i) (k).L[(i) * (k).ls]
 
+// (Cached blocks are the 6 generator rows of a body: joint limits are visited through memory,
+// gs_visit_limit, so no other size exists; k.n is 6 whenever k.g >= 0.)
 ARB_D void gs_cache_flush(const DevModel& m, const DevBatch& b, int64_t w, GsCache& k) {
   const int NG = m.ngrows;
   if (k.g < 0) return;
   bool any = false;
 #pragma unroll
-  for (int p = 0; p < 6; ++p) any = any || (p < k.n && k.dy[p] != 0.);
+  for (int p = 0; p < 6; ++p) any = any || (k.dy[p] != 0.);
   double* pu = b.fu + k.g * ARB_TILE;
   if (any) {
     // (the accumulated wrench y is not maintained during the sweeps: gs_final_wrench forms it from
@@ -316,52 +318,30 @@ ARB_D void gs_cache_flush(const DevModel& m, const DevBatch& b, int64_t w, GsCac
     // Rows outside the block, four at a time: the loads of four rows are in flight together
     // (the switch is bound by memory latency), and the loop is NOT unrolled further -- this code
     // sits in the sweep loop, whose instructions must fit the SM's 32 KB instruction cache
-    // together with the sliding solve.  Row i of the outside rows is i (< g) or i + n.
-    const int nout = NG - k.n;
-    if (k.n == 6) {
+    // together with the sliding solve.  Row i of the outside rows is i (< g) or i + 6.
+    const int nout = NG - 6;
 #pragma unroll 1
-      for (int i0 = 0; i0 < nout; i0 += 4) {
-        double acc[4], uu[4];
-        int rr[4];
+    for (int i0 = 0; i0 < nout; i0 += 4) {
+      double acc[4], uu[4];
+      int rr[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int ii = i0 + i < nout ? i0 + i : nout - 1;
-          rr[i] = ii < k.g ? ii : ii + 6;
-          const double* q = pl + rr[i] * rowstride;
-          uu[i] = b.fu[rr[i] * ARB_TILE];       // (in flight with the Lambda rows: one round trip, not two)
-          double a = 0.;
+      for (int i = 0; i < 4; ++i) {
+        const int ii = i0 + i < nout ? i0 + i : nout - 1;
+        rr[i] = ii < k.g ? ii : ii + 6;
+        const double* q = pl + rr[i] * rowstride;
+        uu[i] = b.fu[rr[i] * ARB_TILE];       // (in flight with the Lambda rows: one round trip, not two)
+        double a = 0.;
 #pragma unroll
-          for (int p = 0; p < 6; ++p) a += q[p * ARB_TILE] * k.dy[p];
-          acc[i] = a;
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i0 + i < nout) b.fu[rr[i] * ARB_TILE] = uu[i] + acc[i];
+        for (int p = 0; p < 6; ++p) a += q[p * ARB_TILE] * k.dy[p];
+        acc[i] = a;
       }
-    } else {
-#pragma unroll 1
-      for (int i0 = 0; i0 < nout; i0 += 4) {
-        double lam[4], uu[4];
-        int rr[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int ii = i0 + i < nout ? i0 + i : nout - 1;
-          rr[i] = ii < k.g ? ii : ii + 1;
-          lam[i] = pl[rr[i] * rowstride];
-          uu[i] = b.fu[rr[i] * ARB_TILE];
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i0 + i < nout) b.fu[rr[i] * ARB_TILE] = uu[i] + lam[i] * k.dy[0];
-      }
+      for (int i = 0; i < 4; ++i)
+        if (i0 + i < nout) b.fu[rr[i] * ARB_TILE] = uu[i] + acc[i];
     }
   }
-  if (k.n == 6) {
 #pragma unroll
-    for (int p = 0; p < 6; ++p) pu[p * ARB_TILE] = k.u[p];
-  } else {
-    pu[0] = k.u[0];
-  }
+  for (int p = 0; p < 6; ++p) pu[p * ARB_TILE] = k.u[p];
   k.g = -1;
 }
 
@@ -369,25 +349,18 @@ template <bool WITH_U>
 ARB_D void gs_cache_load(const DevModel& m, const DevBatch& b, int64_t w, GsCache& k, int g, int n) {
   const int NG = m.ngrows;
   k.g = g;
-  k.n = n;
+  k.n = 6;
   const double* pu = b.fu + g * ARB_TILE;
   const double* pl = b.fLam + (g * NG + g) * ARB_TILE;
   const int rowstride = NG * ARB_TILE;
 #pragma unroll
   for (int p = 0; p < 6; ++p) k.dy[p] = 0.;
-  if (n == 6) {
 #pragma unroll
-    for (int p = 0; p < 6; ++p) {
-      k.u[p] = WITH_U ? pu[p * ARB_TILE] : 0.;
+  for (int p = 0; p < 6; ++p) {
+    k.u[p] = WITH_U ? pu[p * ARB_TILE] : 0.;
 #pragma unroll
-      for (int q = 0; q < 6; ++q) GSL(k, 6 * p + q) = pl[q * ARB_TILE];
-      pl += rowstride;
-    }
-  } else {      // a 1-row block only ever uses element 0 of L, u and dy
-#pragma unroll
-    for (int p = 1; p < 6; ++p) k.u[p] = 0.;
-    GSL(k, 0) = pl[0];
-    k.u[0] = WITH_U ? pu[0] : 0.;
+    for (int q = 0; q < 6; ++q) GSL(k, 6 * p + q) = pl[q * ARB_TILE];
+    pl += rowstride;
   }
 }
 
@@ -404,93 +377,62 @@ ARB_D void gs_cache_switch(const DevModel& m, const DevBatch& b, int64_t w, GsCa
     if (g2 >= 0) gs_cache_load<true>(m, b, w, k, g2, n2);
     return;
   }
-  const int NG = m.ngrows, g = k.g, n = k.n;
+  const int NG = m.ngrows, g = k.g;
   const int rowstride = NG * ARB_TILE;
   bool any = false;
 #pragma unroll
-  for (int p = 0; p < 6; ++p) any = any || (p < n && k.dy[p] != 0.);
+  for (int p = 0; p < 6; ++p) any = any || (k.dy[p] != 0.);
   double un[6];
   const double* pun = b.fu + g2 * ARB_TILE;
   const double* plg = b.fLam + (g2 * NG + g2) * ARB_TILE;      // Lambda[g2 + p, g2 + q]
   const double* plf = b.fLam + (g2 * NG + g) * ARB_TILE;       // Lambda[g2 + p, g + q]
   double* pu = b.fu + g * ARB_TILE;
-  if (n2 == 6) {
+#pragma unroll
+  for (int p = 0; p < 6; ++p) {
+    un[p] = pun[p * ARB_TILE];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) GSL(k, 6 * p + q) = plg[p * rowstride + q * ARB_TILE];
+  }
+  if (any) {
 #pragma unroll
     for (int p = 0; p < 6; ++p) {
-      un[p] = pun[p * ARB_TILE];
+      double a = 0.;
 #pragma unroll
-      for (int q = 0; q < 6; ++q) GSL(k, 6 * p + q) = plg[p * rowstride + q * ARB_TILE];
+      for (int q = 0; q < 6; ++q) a += plf[p * rowstride + q * ARB_TILE] * k.dy[q];
+      un[p] = un[p] + a;
     }
-    if (any) {
-      if (n == 6) {
-#pragma unroll
-        for (int p = 0; p < 6; ++p) {
-          double a = 0.;
-#pragma unroll
-          for (int q = 0; q < 6; ++q) a += plf[p * rowstride + q * ARB_TILE] * k.dy[q];
-          un[p] = un[p] + a;
-        }
-      } else {
-#pragma unroll
-        for (int p = 0; p < 6; ++p) un[p] = un[p] + plf[p * rowstride] * k.dy[0];
-      }
-    }
-  } else {
-    un[0] = pun[0];
-#pragma unroll
-    for (int p = 1; p < 6; ++p) un[p] = 0.;
-    GSL(k, 0) = plg[0];
-    if (any) {
-      if (n == 6) {
-        double a = 0.;
-#pragma unroll
-        for (int q = 0; q < 6; ++q) a += plf[q * ARB_TILE] * k.dy[q];
-        un[0] = un[0] + a;
-      } else {
-        un[0] = un[0] + plf[0] * k.dy[0];
-      }
-    }
-  }
-  if (any) {     // the rows outside both blocks, as in gs_cache_flush
+    // the rows outside both blocks, as in gs_cache_flush
     const double* pl = b.fLam + g * ARB_TILE;
-    const int nrest = NG - n - n2;
-    const int lo = g < g2 ? g : g2, nlo = g < g2 ? n : n2, hi = g < g2 ? g2 : g, nhi = g < g2 ? n2 : n;
+    const int nrest = NG - 12;
+    const int lo = g < g2 ? g : g2, hi = g < g2 ? g2 : g;
 #pragma unroll 1
     for (int i0 = 0; i0 < nrest; i0 += 4) {
-      double acc[4], uu[4];
+      double acc[4];
       int rr[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         int r = i0 + i < nrest ? i0 + i : nrest - 1;
-        if (r >= lo) r += nlo;
-        if (r >= hi) r += nhi;
+        if (r >= lo) r += 6;
+        if (r >= hi) r += 6;
         rr[i] = r;
         const double* q = pl + r * rowstride;
-        uu[i] = b.fu[r * ARB_TILE];
-        if (n == 6) {
-          double a = 0.;
+        const double uu = b.fu[r * ARB_TILE];
+        double a = 0.;
 #pragma unroll
-          for (int p = 0; p < 6; ++p) a += q[p * ARB_TILE] * k.dy[p];
-          acc[i] = uu[i] + a;
-        } else {
-          acc[i] = uu[i] + q[0] * k.dy[0];
-        }
+        for (int p = 0; p < 6; ++p) a += q[p * ARB_TILE] * k.dy[p];
+        acc[i] = uu + a;
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         if (i0 + i < nrest) b.fu[rr[i] * ARB_TILE] = acc[i];
     }
   }
-  if (n == 6) {
 #pragma unroll
-    for (int p = 0; p < 6; ++p) pu[p * ARB_TILE] = k.u[p];
-  } else {
-    pu[0] = k.u[0];
-  }
+  for (int p = 0; p < 6; ++p) pu[p * ARB_TILE] = k.u[p];
 #pragma unroll
   for (int p = 0; p < 6; ++p) { k.u[p] = un[p]; k.dy[p] = 0.; }
   k.g = g2;
-  k.n = n2;
+  k.n = 6;
 }
 
 // one visit of a constraint that touches TWO generator bodies (e.g. a ball-and-socket joint
@@ -895,13 +837,13 @@ ARB_D void gs_visit_limit(const DevModel& m, const DevBatch& b, int c, double dt
   if (k.g >= 0) {
     bool any = false;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) any = any || (i < k.n && k.dy[i] != 0.);
+    for (int i = 0; i < 6; ++i) any = any || (k.dy[i] != 0.);
     if (any) {
       const double* pl = b.fLam + (g * NG + k.g) * ARB_TILE;
       double acc = 0.;
 #pragma unroll
       for (int i = 0; i < 6; ++i)
-        if (i < k.n) acc += pl[i * ARB_TILE] * k.dy[i];
+        acc += pl[i * ARB_TILE] * k.dy[i];
       v = v + acc;
     }
   }
@@ -916,10 +858,11 @@ ARB_D void gs_visit_limit(const DevModel& m, const DevBatch& b, int c, double dt
   FT(b.fbranch, c) = br;
   if (df != 0.) {
     const double* col = b.fLam + g * ARB_TILE;          // Lambda[r, g] = col[r rowstride]
-    const int kg = k.g, kn = k.g >= 0 ? k.n : 0;
+    const int kg = k.g, kn = k.g >= 0 ? 6 : 0;
+    if (kg >= 0) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i)
-      if (i < kn) k.u[i] += col[(kg + i) * rowstride] * df;
+      for (int i = 0; i < 6; ++i) k.u[i] += col[(kg + i) * rowstride] * df;
+    }
     const int nout = NG - kn;
 #pragma unroll 1
     for (int i0 = 0; i0 < nout; i0 += 4) {
