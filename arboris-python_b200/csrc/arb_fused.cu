@@ -58,6 +58,9 @@ struct FusedState {
 #ifndef GS_STAGE_CARVEOUT
 #define GS_STAGE_CARVEOUT 40   /* per cent of the SM's 228 KB for shared memory: 2 CTAs x 43 KB (A/B builds) */
 #endif
+#ifndef GS_STAGE_PLAIN
+#define GS_STAGE_PLAIN 1       /* 0: always the general instantiation of the staged kernel (A/B builds) */
+#endif
 #ifndef GS_CARVEOUT
 #define GS_CARVEOUT 0          /* the unstaged kernel uses no shared memory (A/B builds: what a smaller L1 costs) */
 #endif
@@ -106,7 +109,7 @@ __global__ void __launch_bounds__(THREADS, GS_MINBLOCKS) k_fused_gs(DevModel m, 
 }
 // Gauss-Seidel with the contact operands staged by TMA (world_fused_gs_staged): 10 KB of shared memory
 // and one mbarrier per warp, a 64-byte descriptor per constraint
-template <int THREADS>
+template <int THREADS, bool PLAIN>
 __global__ void __launch_bounds__(THREADS, GS_MINBLOCKS) k_fused_gs_staged(DevModel m, DevBatch b, double dt) {
   __shared__ __align__(128) double sbuf[(THREADS / 32) * (GS_STAGE_WARP_BYTES / 8)];
   __shared__ __align__(16) GsDesc sdesc[32];
@@ -138,14 +141,16 @@ __global__ void __launch_bounds__(THREADS, GS_MINBLOCKS) k_fused_gs_staged(DevMo
   const bool valid = s < b.W;
   const int64_t sv = valid ? s : b.W - 1;
   double Lr[36];
-  const unsigned long long key = world_fused_gs_staged(m, fused_tile_view(b, sv), sv, valid, dt, Lr, 1, st);
+  const unsigned long long key = world_fused_gs_staged<PLAIN>(m, fused_tile_view(b, sv), sv, valid, dt, Lr, 1, st);
   if (valid && b.fkey != nullptr) b.fkey[s] = key;
 }
 static void launch_gs(const arb_batch* b, const DevBatch& d, double dt) {
   const int64_t W = d.W;
   const unsigned grid = (unsigned)((W + GS_THREADS - 1) / GS_THREADS);
-  if (b->gs_stage && b->m.nc <= 32)
-    k_fused_gs_staged<GS_THREADS><<<grid, GS_THREADS, 0, b->stream>>>(b->m, d, dt);
+  if (b->gs_stage && b->m.nc <= 32) {
+    if (b->gs_plain) k_fused_gs_staged<GS_THREADS, true><<<grid, GS_THREADS, 0, b->stream>>>(b->m, d, dt);
+    else k_fused_gs_staged<GS_THREADS, false><<<grid, GS_THREADS, 0, b->stream>>>(b->m, d, dt);
+  }
   else
     k_fused_gs<GS_THREADS><<<grid, GS_THREADS, 0, b->stream>>>(b->m, d, dt);
 }
@@ -281,7 +286,19 @@ static int ensure_fused_scratch(arb_batch* b) {
   // the per-lane stages live on L1 (operands re-read every sweep / pass): no shared-memory carve-out
   CUDA_OKF(cudaFuncSetAttribute(k_fused_gs<GS_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, GS_L_SMEM ? 20 : GS_CARVEOUT));
   // (staged: 2 CTAs x 43 KB per SM; the driver rounds the carve-out up to the next configuration)
-  CUDA_OKF(cudaFuncSetAttribute(k_fused_gs_staged<GS_THREADS>, cudaFuncAttributePreferredSharedMemoryCarveout, GS_STAGE_CARVEOUT));
+  CUDA_OKF(cudaFuncSetAttribute(k_fused_gs_staged<GS_THREADS, false>, cudaFuncAttributePreferredSharedMemoryCarveout, GS_STAGE_CARVEOUT));
+  CUDA_OKF(cudaFuncSetAttribute(k_fused_gs_staged<GS_THREADS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, GS_STAGE_CARVEOUT));
+  {   // the plain instantiation serves models of joint limits and contact-aligned one-body contacts only
+    const HostModel& hm = b->model->host;
+    bool plain = GS_STAGE_PLAIN != 0;
+    for (int c = 0; c < hm.nc; ++c) {
+      const bool lim = hm.ctype[c] == ARB_CONS_JOINT_LIMITS;
+      const bool alc = hm.ctype[c] == ARB_CONS_SOFT_FINGER_PLANE_POINT && hm.caligned[c] != 0 &&
+                       ((hm.cgen1[c] >= 0) != (hm.cgen0[c] >= 0));
+      plain = plain && (lim || alc);
+    }
+    b->gs_plain = plain ? 1 : 0;
+  }
   CUDA_OKF(cudaFuncSetAttribute(k_fused_prepare_lane, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   CUDA_OKF(cudaFuncSetAttribute(k_fused_finish, cudaFuncAttributePreferredSharedMemoryCarveout, 0));
   b->fused = f;

@@ -1162,6 +1162,7 @@ __device__ __forceinline__ int softfinger_begin_tiled(const double* v, const dou
 
 // gs_visit_one_body<4> with staged operands.  vmask: the lanes of the warp that take part in this
 // visit (all of them are here); cn: the warp's next staged contact (-1: none left).
+template <bool PLAIN>
 __device__ __forceinline__ int gs_visit_contact_staged(const DevBatch& b, int c, double dt, GsCache& k, int* status,
                                                        const GsStage& st, unsigned vmask, int cn) {
   const GsDesc& d = st.desc[c];
@@ -1169,7 +1170,7 @@ __device__ __forceinline__ int gs_visit_contact_staged(const DevBatch& b, int c,
   const double* Tg = (side0 ? b.fT0 : b.fT1) + c * (24 * ARB_TILE);
   const double sign = side0 ? -1. : 1.;
   double* pf = b.ff + d.row * ARB_TILE;
-  const bool al = d.aligned != 0;
+  const bool al = PLAIN || d.aligned != 0;
   const double* sA = st.buf + st.lane;
   const double* sP = sA + 16 * ARB_TILE;
   const double* sAux = sA + 32 * ARB_TILE;
@@ -1259,6 +1260,10 @@ __device__ __forceinline__ void gs_desc_fill(const DevModel& m, GsDesc* desc, in
 
 // All 32 lanes of the warp call this together (valid = false: a lane beyond the batch, given the view
 // of the last world and kept from writing); m.nc <= 32.
+// PLAIN: the model holds nothing but joint limits and contacts of contact-aligned bodies (human36 on a
+// ground plane): the instantiation without the general visits (ball-and-socket, two-body constraints,
+// 4x6 contact maps), whose code the sweep loop then does not carry through the instruction cache.
+template <bool PLAIN>
 __device__ unsigned long long world_fused_gs_staged(const DevModel& m, const DevBatch& b, int64_t w, bool valid, double dt,
                                                     double* Lstore, int Lstride, GsStage& st) {
   const unsigned FULL = 0xffffffffu;
@@ -1372,11 +1377,11 @@ __device__ unsigned long long world_fused_gs_staged(const DevModel& m, const Dev
 #endif
         if (d.type == ARB_CONS_JOINT_LIMITS) {
           gs_visit_limit(m, b, c, dt, k);
-        } else if (d.gneed < 0) {
+        } else if (!PLAIN && d.gneed < 0) {
           gs_visit_two_body(m, b, w, c, dt, &status);
-        } else if (d.type == ARB_CONS_BALL_SOCKET) {
+        } else if (!PLAIN && d.type == ARB_CONS_BALL_SOCKET) {
           gs_visit_one_body<3>(m, b, w, c, dt, k, &status);
-        } else if (gs_visit_contact_staged(b, c, dt, k, &status, st, vmask, cn) == 3) {
+        } else if (gs_visit_contact_staged<PLAIN>(b, c, dt, k, &status, st, vmask, cn) == 3) {
           slid |= 1u << c;
         }
       }
