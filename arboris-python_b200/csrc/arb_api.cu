@@ -178,6 +178,7 @@ extern "C" int arb_batch_set_option(arb_batch* b, const char* name, int value) {
   if (s == "force_phases") b->force_phases = value;
   else if (s == "gs_coop") b->gs_coop = value;
   else if (s == "gs_stage") b->gs_stage = value;
+  else if (s == "gs_plain") b->gs_plain_allow = value;
   else if (s == "sort_period") b->sort_period = value < 0 ? 0 : value;
   else if (s == "prepare_group") b->prepare_group = value;
   else if (s == "time_stages") {

@@ -290,7 +290,7 @@ static int ensure_fused_scratch(arb_batch* b) {
   CUDA_OKF(cudaFuncSetAttribute(k_fused_gs_staged<GS_THREADS, true>, cudaFuncAttributePreferredSharedMemoryCarveout, GS_STAGE_CARVEOUT));
   {   // the plain instantiation serves models of joint limits and contact-aligned one-body contacts only
     const HostModel& hm = b->model->host;
-    bool plain = GS_STAGE_PLAIN != 0;
+    bool plain = GS_STAGE_PLAIN != 0 && b->gs_plain_allow != 0;
     for (int c = 0; c < hm.nc; ++c) {
       const bool lim = hm.ctype[c] == ARB_CONS_JOINT_LIMITS;
       const bool alc = hm.ctype[c] == ARB_CONS_SOFT_FINGER_PLANE_POINT && hm.caligned[c] != 0 &&

@@ -31,6 +31,7 @@ struct arb_batch {
   int gs_stage = 1;                // 1 (default): Gauss-Seidel kernel with the contact operands staged in shared memory by TMA
                                    // (world_fused_gs_staged; models of at most 32 constraints), 0: operands loaded from global memory
   int gs_plain = 0;                // set by the fused state: the model qualifies for the plain instantiation of the staged kernel
+  int gs_plain_allow = 1;          // option gs_plain (set before the first step): 0 keeps the general instantiation
   int time_stages = 0;             // 1: CUDA events around every fused stage (diagnostic, synchronises per step)
   double stage_ms[4] = {0., 0., 0., 0.};   // accumulated prepare / gs / finish milliseconds, [3] = steps timed
   FusedState* fused = nullptr;

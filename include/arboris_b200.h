@@ -147,6 +147,9 @@ int arb_batch_set_stream(arb_batch *batch, void *stream);
  *                 copied there one visit ahead by TMA bulk copies (models of at most 32
  *                 constraints; larger ones run the other kernel); 0: the kernel that loads them
  *                 from global memory; bit-identical results;
+ *  "gs_plain"     0 (before the batch's first step): the staged kernel's general instantiation even
+ *                 for a model that qualifies for the plain one (joint limits and one-body contacts of
+ *                 contact-aligned bodies only); bit-identical results, a test switch;
  *  "gs_coop"      1: block-cooperative Gauss-Seidel kernel (sliding solves pooled through
  *                 shared memory) instead of the per-lane one; bit-identical results;
  *  "prepare_group" 1: the prepare stage runs with a group of 16 lanes per world and the world's

@@ -235,17 +235,18 @@ def test_staged_gs_bit_identical(torch_cuda):
     memory (TMA bulk copies, option gs_stage) does the same arithmetic in the same order as the
     kernel that loads them from global memory: states, forces, branches after 120 steps of falling
     humanoids are equal bit for bit, for a batch that is not a multiple of the warp size, with and
-    without world sorting."""
+    without world sorting, in the plain and in the general instantiation of the staged kernel."""
     from arboris_b200 import scenarios
     from arboris_b200.flatten import flatten
     model = flatten(scenarios.BUILDERS["human36_contact"]())
     W = 1003
     gpos, gvel = scenarios.initial_states(model, "human36_contact", 0, W)
     out = []
-    for stage, sort in ((1, 2), (0, 2), (1, 0)):
+    for stage, sort, plain in ((1, 2, 1), (0, 2, 1), (1, 0, 1), (1, 2, 0)):
         bw = _batch(model, W)
         bw.set_option("gs_stage", stage)
         bw.set_option("sort_period", sort)
+        bw.set_option("gs_plain", plain)     # (0: the general instantiation of the staged kernel)
         bw.set_state(gpos, gvel)
         bw.step(1e-3, 120)
         out.append(bw.get_state() + (bw.constraints("branch").cpu().numpy(), bw.status().cpu().numpy()))
