@@ -44,3 +44,33 @@ def test_auto_chunks_follow_batch_size():
     assert HostPipeline.auto_chunks(32768) == 1
     assert HostPipeline.auto_chunks(131072) == (1, 2, 1)
     assert HostPipeline.auto_chunks(262144) == (1, 1, 2, 2, 2, 1, 1)
+
+
+def test_traffic_json_follows_from_the_committed_ncu_summaries():
+    """profiles/traffic.json (what bench.py reports as roofline.traffic and frac_executed) can be
+    recomputed from the ncu summaries committed beside it (profiles/make_traffic.py)."""
+    import importlib.util
+    import json
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    prof = os.path.join(root, "profiles")
+    doc = json.load(open(os.path.join(prof, "traffic.json")))["human36_contact"]
+    tag = re.search(r"profiles/(\w+)_ncu_", doc["source"]).group(1)
+    spec = importlib.util.spec_from_file_location("make_traffic", os.path.join(prof, "make_traffic.py"))
+    mt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mt)
+    W = 262144
+    tot_b = tot_f = 0.
+    for st in ("prepare", "gs", "finish"):
+        r = mt.read(os.path.join(prof, "%s_ncu_%s_%d.txt" % (tag, st, W)))
+        b = (r["dram__bytes_read.sum"] + r["dram__bytes_write.sum"])/W
+        f = (2*r["smsp__sass_thread_inst_executed_op_dfma_pred_on.sum"]
+             + r["smsp__sass_thread_inst_executed_op_dmul_pred_on.sum"]
+             + r["smsp__sass_thread_inst_executed_op_dadd_pred_on.sum"])/W
+        assert abs(doc["per_kernel_bytes_per_world"][r["kernel"]] - b) <= 1e-9*b
+        assert abs(doc["per_kernel_executed_fp64_flop_per_world"][r["kernel"]] - f) <= 1e-9*f
+        tot_b += b
+        tot_f += f
+    assert abs(doc["dram_bytes_per_world_step"] - tot_b) <= 1e-9*tot_b
+    assert abs(doc["executed_fp64_flop_per_world_step"] - tot_f) <= 1e-9*tot_f
