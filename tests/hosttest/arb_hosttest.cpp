@@ -184,6 +184,25 @@ int ht_sliding_root(const double* A, const double* alpha, double mu, double* s, 
   *found = f ? 1 : 0;
   return ok ? 1 : 0;
 }
+// the sextic routines of the sliding root, one polynomial at a time (p[0..5], monic)
+int ht_poly6_positive(const double* p) { return poly6_positive_on_halfline(p) ? 1 : 0; }
+int ht_poly6_fast(const double* p, double* root) {
+  double c[7];      // (the bracket refinement reads the leading coefficient too)
+  for (int k = 0; k < 6; ++k) c[k] = p[k];
+  c[6] = 1.;
+  return poly6_largest_root_fast(c, root);
+}
+int ht_poly6_slow(const double* p, double* root) {
+  double T = 0.;
+  for (int k = 0; k < 6; ++k) T = fmax(T, fabs(p[k]));
+  T += 1.;
+  double roots[6], c[7];
+  for (int k = 0; k < 6; ++k) c[k] = p[k];
+  c[6] = 1.;
+  const int nr = poly6_roots_slow(c, T, roots);
+  if (nr) *root = roots[nr - 1];
+  return nr;
+}
 long ht_fastroot_hits() { return arb_fastroot_hits; }
 long ht_fastroot_fail(int i) { return arb_fastroot_fail[i]; }
 void ht_set_slidemask(unsigned* p) { arb_dbg_slidemask = p; }

@@ -320,3 +320,65 @@ def test_group_prepare_vs_real_reference(name, tol):
     assert not hb.iarr("status").any()
     for k, v in worst.items():
         assert v <= tol, (k, v)
+
+
+def _poly6_lib():
+    L = harness.lib()
+    dp = C.POINTER(C.c_double)
+    L.ht_poly6_positive.argtypes = [dp]
+    L.ht_poly6_fast.argtypes = [dp, dp]
+    L.ht_poly6_slow.argtypes = [dp, dp]
+    return L, dp
+
+
+def _random_sextic(rng, nreal):
+    """Monic sextic with `nreal` real roots (0, 2, 4 or 6) and conjugate pairs for the rest, scaled like
+    the sliding-friction polynomials (coefficients O(1))."""
+    roots = list(rng.uniform(-2., 2., size=nreal))
+    for _ in range((6 - nreal)//2):
+        re, im = rng.uniform(-2., 2.), rng.uniform(0.05, 2.)
+        roots += [complex(re, im), complex(re, -im)]
+    c = np.real(np.poly(roots))          # highest degree first, c[0] = 1
+    return np.ascontiguousarray(c[::-1][:6]), np.array(roots)
+
+
+def test_positivity_march_never_claims_a_polynomial_with_a_root():
+    """poly6_positive_on_halfline (the proof that the sliding problem has no admissible root, the
+    reference's s = -1e10 clamp) is a sufficient test: it must never hold for a sextic with a root t >= 0,
+    and it should hold for the clearly positive ones."""
+    L, dp = _poly6_lib()
+    rng = np.random.default_rng(11)
+    proven = total_pos = 0
+    for trial in range(4000):
+        p, roots = _random_sextic(rng, int(rng.choice([0, 2, 4, 6])))
+        real = roots[np.abs(np.imag(roots)) == 0].real
+        has_root = bool((real >= 0.).any())
+        ok = L.ht_poly6_positive(p.ctypes.data_as(dp))
+        if has_root:
+            assert not ok, (trial, p, real)
+        else:
+            total_pos += 1
+            proven += ok
+    assert total_pos > 500 and proven > 0.9*total_pos, (proven, total_pos)
+
+
+def test_fast_root_with_bracket_recovery_is_the_largest_real_root():
+    """poly6_largest_root_fast (Laguerre from the Samuelson bound, an iterate left of a root refined in
+    its bracket, certificate): whenever it answers, the answer is the largest real root -- checked
+    against numpy.roots and against the rigorous isolation."""
+    L, dp = _poly6_lib()
+    rng = np.random.default_rng(12)
+    answered = 0
+    for trial in range(4000):
+        p, roots = _random_sextic(rng, int(rng.choice([2, 4, 6, 6])))
+        r = np.roots(np.concatenate(([1.], p[::-1])))
+        real = np.sort(r[np.abs(r.imag) < 1e-9*np.maximum(1., np.abs(r))].real)
+        t = C.c_double(0.)
+        if L.ht_poly6_fast(p.ctypes.data_as(dp), C.byref(t)):
+            answered += 1
+            assert len(real) > 0 and abs(t.value - real[-1]) <= 1e-7*max(1., abs(real[-1])), (trial, t.value, real)
+        ts = C.c_double(0.)
+        nr = L.ht_poly6_slow(p.ctypes.data_as(dp), C.byref(ts))
+        if nr and len(real) and real[-1] > 1e-6:
+            assert abs(ts.value - real[-1]) <= 1e-7*max(1., abs(real[-1])), (trial, ts.value, real)
+    assert answered > 2000
