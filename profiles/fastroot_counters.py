@@ -31,8 +31,9 @@ f = [L.ht_fastroot_fail(i) for i in range(8)]
 tot = hits + sum(f[:5])
 print("%d worlds x %d steps in %.1f s: %d sliding solves; certified by the fast path %d (%.3f %%)" %
       (W, T, time.time() - t0, tot, hits, 100.*hits/max(tot, 1)))
-print("left for the rigorous isolation: variance < 0 / NaN %d, left of a root %d, discriminant / slope %d, "
+print("left the fast path: variance < 0 / NaN %d, left of a root %d, discriminant / slope %d, "
       "no convergence %d, certificate %d  (%.3f %% in all)" % (f[0], f[1], f[2], f[3], f[4], 100.*sum(f[:5])/max(tot, 1)))
-print("recoveries: bracket refinements inside the fast path %d, no root t >= 0 proven by the positivity march %d; Laguerre iterations per solve %.2f" %
-      (f[5], f[6], f[7]/max(tot, 1)))
+print("recoveries: bracket refinements inside the fast path %d; of those that left it, no root t >= 0 proven by the "
+      "positivity march %d, rigorous isolation %d (%.4f %% of the solves); Laguerre iterations per solve %.2f" %
+      (f[5], f[6], sum(f[:5]) - f[6], 100.*(sum(f[:5]) - f[6])/max(tot, 1), f[7]/max(tot, 1)))
 print("finite:", bool(np.isfinite(hb.gvel).all()), " checksum gvel %.17g" % float(np.abs(hb.gvel).sum()))
